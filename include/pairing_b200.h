@@ -1,0 +1,160 @@
+/* pairing_b200.h -- C ABI of the B200-native batched BLS12-381 pairing / wNAF engine.
+ *
+ * This is the drop-in boundary beneath the `pairing` crate's trait surface (v0.14.2).  The
+ * reference has no FFI of its own: its boundary is the Rust traits `Engine` (src/lib.rs:34-110),
+ * `CurveProjective` (src/lib.rs:114-181), `CurveAffine` (src/lib.rs:185-234) and `Wnaf`
+ * (src/wnaf.rs:75-179).  Each entry point below names the reference routine it replaces; the Rust
+ * shim that binds them is shown in INTEGRATION.md and rust/src/ffi.rs.
+ *
+ * Data layout (all little-endian, identical byte-for-byte to the crate's in-memory values):
+ *   Fq      6 x u64 limbs, Montgomery form (x * 2^384 mod q), always < q   (bls12_381/fq.rs:510,699)
+ *   Fq2     c0 | c1                                                        (fq2.rs:8-12)
+ *   Fq6     c0 | c1 | c2                                                   (fq6.rs:8-12)
+ *   Fq12    c0 | c1                                                        (fq12.rs:8-12)
+ *   FrRepr  4 x u64 limbs, canonical integer, NOT Montgomery               (fr.rs:58)
+ * Ownership: the caller owns every buffer; nothing is retained after a call returns.
+ * Errors: every function returns 0 on success or a negative bls_status; nothing unwinds across
+ * the ABI.  There is no CPU fallback: without a CUDA device bls_ctx_create fails.
+ * Threading: calls on one bls_ctx must be serialised by the caller (one ordered stream per device).
+ */
+#ifndef PAIRING_B200_H
+#define PAIRING_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { uint64_t l[6]; } bls_fq;
+typedef struct { bls_fq c0, c1; } bls_fq2;
+typedef struct { bls_fq2 c0, c1, c2; } bls_fq6;
+typedef struct { bls_fq6 c0, c1; } bls_fq12;                       /* 576 B */
+typedef struct { bls_fq x, y; uint64_t infinity; } bls_g1_affine;  /* 104 B; ec.rs:13-18 */
+typedef struct { bls_fq x, y, z; } bls_g1;                         /* 144 B; Jacobian, z == 0 <=> infinity; ec.rs:31-36 */
+typedef struct { bls_fq2 x, y; uint64_t infinity; } bls_g2_affine; /* 200 B */
+typedef struct { bls_fq2 x, y, z; } bls_g2;                        /* 288 B */
+typedef struct { uint64_t l[4]; } bls_fr_repr;                     /* 32 B */
+/* G2Prepared (ec.rs:1615-1619): 68 = 63 doubling + 5 addition coefficient triples in loop order */
+typedef struct { bls_fq2 coeffs[68][3]; uint64_t infinity; } bls_g2_prepared; /* 19 592 B */
+
+typedef struct bls_ctx bls_ctx;
+
+typedef enum {
+  BLS_OK = 0,
+  BLS_ERR_INVALID_ARGUMENT = -1,
+  BLS_ERR_NO_DEVICE = -2,
+  BLS_ERR_CUDA = -3,
+  BLS_ERR_OUT_OF_MEMORY = -4,
+  BLS_ERR_UNSUPPORTED = -5
+} bls_status;
+
+/* One context = one CUDA device + one ordered stream + reusable device scratch.  `device` is a CUDA
+ * ordinal.  Multi-GPU callers create one context per device (one process per GPU under
+ * torch.distributed / NCCL, or several contexts in one process) and shard batches themselves;
+ * see bls_fq12_product for the only cross-device reduction the path has. */
+bls_ctx* bls_ctx_create(int device, int* err);
+void bls_ctx_destroy(bls_ctx* ctx);
+const char* bls_strerror(int status);
+/* text of the last CUDA error seen by this context (empty string if none) */
+const char* bls_ctx_last_error(const bls_ctx* ctx);
+int bls_ctx_device(const bls_ctx* ctx);
+int bls_ctx_sm_count(const bls_ctx* ctx);
+/* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
+uint64_t bls_ctx_launch_count(const bls_ctx* ctx);
+
+/* ------------------------------------------------------------------ pairing engine (host buffers) */
+
+/* G2Affine::prepare / G2Prepared::from_affine, bls12_381/mod.rs:168-358, for n points. */
+int bls_g2_prepare_batch(bls_ctx*, const bls_g2_affine* q, bls_g2_prepared* out, size_t n);
+/* n independent Engine::miller_loop(&[(&p_i.prepare(), &q_i.prepare())]), mod.rs:40-102.
+ * Pairs with an infinity member give Fq12::one() (mod.rs:49-54). */
+int bls_miller_loop_batch(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n);
+/* same, from already prepared G2 coefficients (the reference's actual miller_loop signature) */
+int bls_miller_loop_prepared_batch(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q, bls_fq12* out, size_t n);
+/* ONE Engine::miller_loop over n pairs: the product of the n Miller values (mod.rs:80-95). */
+int bls_multi_miller_loop(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1);
+int bls_multi_miller_loop_prepared(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q, size_t n, bls_fq12* out1);
+/* Engine::final_exponentiation, mod.rs:104-160; is_some[i] = 0 marks the reference's None (input 0),
+ * in which case out[i] is all-zero.  is_some may be NULL. */
+int bls_final_exponentiation_batch(bls_ctx*, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n);
+/* Engine::pairing on affine inputs, lib.rs:101-109 (Miller loop + final exponentiation). */
+int bls_pairing_batch(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n);
+/* product of n Fq12 values (Fq12::mul_assign, fq12.rs:116-130): merges per-device partial Miller
+ * products before the single final exponentiation of a sharded multi_miller_loop. */
+int bls_fq12_product(bls_ctx*, const bls_fq12* in, size_t n, bls_fq12* out1);
+
+/* ------------------------------------------------------------------ curve groups (host buffers) */
+
+/* Wnaf::new().scalar(k_i).base(g_i): window from the scalar (ec.rs:895-905 / 1586-1596),
+ * wnaf_table + wnaf_form + wnaf_exp (wnaf.rs:4-71).  Output Jacobian triples are bit-identical
+ * to the reference's. */
+int bls_g1_wnaf_mul_batch(bls_ctx*, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n);
+int bls_g2_wnaf_mul_batch(bls_ctx*, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n);
+/* same with an explicit window 2..7 (the crate-internal wnaf_table/wnaf_form/wnaf_exp triple) */
+int bls_g1_wnaf_mul_window_batch(bls_ctx*, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n, int window);
+int bls_g2_wnaf_mul_window_batch(bls_ctx*, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n, int window);
+/* CurveProjective::mul_assign (double-and-add), ec.rs:534-553 */
+int bls_g1_mul_batch(bls_ctx*, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n);
+int bls_g2_mul_batch(bls_ctx*, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n);
+/* CurveProjective::batch_normalization, ec.rs:246-294, in place */
+int bls_g1_batch_normalization(bls_ctx*, bls_g1* inout, size_t n);
+int bls_g2_batch_normalization(bls_ctx*, bls_g2* inout, size_t n);
+/* From<projective> for affine / CurveProjective::into_affine, ec.rs:586-619 */
+int bls_g1_into_affine_batch(bls_ctx*, const bls_g1* in, bls_g1_affine* out, size_t n);
+int bls_g2_into_affine_batch(bls_ctx*, const bls_g2* in, bls_g2_affine* out, size_t n);
+/* element-wise group law: op = BLS_PT_*.  b is bls_g1/bls_g2 (ADD, SUB), bls_g*_affine (ADD_MIXED)
+ * or NULL (DOUBLE, NEGATE).  ec.rs:296-532, lib.rs:156-160 */
+enum { BLS_PT_DOUBLE = 0, BLS_PT_ADD = 1, BLS_PT_ADD_MIXED = 2, BLS_PT_NEGATE = 3, BLS_PT_SUB = 6 };
+int bls_g1_op_batch(bls_ctx*, int op, const bls_g1* a, const void* b, bls_g1* out, size_t n);
+int bls_g2_op_batch(bls_ctx*, int op, const bls_g2* a, const void* b, bls_g2* out, size_t n);
+
+/* ------------------------------------------------------------------ field tower (host buffers) */
+/* Element-wise field operations, the `Field` trait methods of src/lib.rs:267-325 on
+ * Fq (degree 1), Fq2 (2), Fq6 (6), Fq12 (12).  `b` is an array of the same element type or NULL.
+ * ok[i] = 0 marks None (inverse of 0, from_repr of a non-canonical value); may be NULL. */
+enum {
+  BLS_OP_ADD = 0, BLS_OP_SUB = 1, BLS_OP_MUL = 2, BLS_OP_SQR = 3, BLS_OP_NEG = 4, BLS_OP_DBL = 5,
+  BLS_OP_INV = 6, BLS_OP_FROM_REPR = 7, BLS_OP_INTO_REPR = 8, BLS_OP_MUL_NONRES = 9,
+  BLS_OP_FROB1 = 10, BLS_OP_FROB2 = 11, BLS_OP_FROB3 = 12, BLS_OP_CONJ = 13,
+  BLS_OP_MUL_BY_014 = 14, /* Fq12 only: sparse operands b.c0.c0, b.c0.c1, b.c1.c1 (fq12.rs:34-48) */
+  BLS_OP_MUL_BY_01 = 15,  /* Fq6 only: b.c0, b.c1 (fq6.rs:68-109) */
+  BLS_OP_MUL_BY_1 = 16    /* Fq6 only: b.c1 (fq6.rs:40-66) */
+};
+int bls_field_op_batch(bls_ctx*, int degree, int op, const void* a, const void* b, void* out, uint8_t* ok, size_t n);
+
+/* ------------------------------------------------------------------ device-pointer variants
+ * Same semantics; every pointer is a device pointer on the context's device, the work is enqueued
+ * on `stream` (a cudaStream_t, NULL = the context's own stream) and NOT synchronised.  `scratch`
+ * arguments are caller-provided device buffers of the stated size (so no allocation happens on the
+ * timed path). */
+int bls_g2_prepare_dev(bls_ctx*, const bls_g2_affine* q, bls_g2_prepared* out, size_t n, void* stream);
+int bls_miller_loop_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream);
+int bls_miller_loop_prepared_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q, bls_fq12* out, size_t n, void* stream);
+int bls_final_exponentiation_dev(bls_ctx*, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n, void* stream);
+int bls_pairing_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream);
+/* scratch: bls_multi_miller_scratch_bytes(ctx, n) bytes */
+size_t bls_multi_miller_scratch_bytes(const bls_ctx*, size_t n);
+int bls_multi_miller_loop_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, void* scratch, void* stream);
+size_t bls_fq12_product_scratch_bytes(const bls_ctx*, size_t n);
+int bls_fq12_product_dev(bls_ctx*, const bls_fq12* in, size_t n, bls_fq12* out1, void* scratch, void* stream);
+int bls_g1_wnaf_mul_dev(bls_ctx*, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n, int window, void* stream);
+int bls_g2_wnaf_mul_dev(bls_ctx*, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n, int window, void* stream);
+/* scratch: bls_batch_normalization_scratch_bytes(ctx, degree, n) bytes; degree 1 = G1, 2 = G2 */
+size_t bls_batch_normalization_scratch_bytes(const bls_ctx*, int degree, size_t n);
+int bls_g1_batch_normalization_dev(bls_ctx*, bls_g1* inout, size_t n, void* scratch, void* stream);
+int bls_g2_batch_normalization_dev(bls_ctx*, bls_g2* inout, size_t n, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------ measurement
+ * Register-resident integer-multiply microbenchmark: the roofline denominator for this path
+ * (MEASURED_PEAKS.json has no integer figure).  variant 0 = independent IMAD.WIDE.U32 chains,
+ * 1 = back-to-back fp_mul (300 MAC32 each), 2 = 32-bit IMAD, 3 = carry-linked
+ * IMAD.WIDE.U32.X rows only (mad.lo.cc / madc.hi.cc chains, no reduction).
+ * Returns multiply-accumulates per second in *macs_per_s and the kernel time in *ms. */
+int bls_imad_peak(bls_ctx*, int variant, int iters, double* macs_per_s, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAIRING_B200_H */

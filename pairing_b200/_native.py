@@ -1,0 +1,309 @@
+"""ctypes binding of libpairing_b200.so (the C ABI of include/pairing_b200.h).
+
+The product path has no CPU fallback: if the CUDA library is missing or no device is present every
+entry point raises.  Nothing here imports or calls the oracle.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpairing_b200.so")
+
+# u64 words per ABI struct
+W_FQ, W_FQ2, W_FQ6, W_FQ12 = 6, 12, 36, 72
+W_G1A, W_G1, W_G2A, W_G2, W_FR, W_G2P = 13, 18, 25, 36, 4, 68 * 3 * 12 + 1
+
+OPS = dict(add=0, sub=1, mul=2, sqr=3, neg=4, dbl=5, inv=6, from_repr=7, into_repr=8, mul_nonres=9,
+           frob1=10, frob2=11, frob3=12, conj=13, mul_by_014=14, mul_by_01=15, mul_by_1=16)
+PT_OPS = dict(double=0, add=1, add_mixed=2, negate=3, sub=6)
+
+# every symbol include/pairing_b200.h declares (tests/test_abi.py checks the header against this list)
+SYMBOLS = [
+    "bls_ctx_create", "bls_ctx_destroy", "bls_strerror", "bls_ctx_last_error", "bls_ctx_device",
+    "bls_ctx_sm_count", "bls_ctx_launch_count",
+    "bls_g2_prepare_batch", "bls_miller_loop_batch", "bls_miller_loop_prepared_batch",
+    "bls_multi_miller_loop", "bls_multi_miller_loop_prepared", "bls_final_exponentiation_batch",
+    "bls_pairing_batch", "bls_fq12_product",
+    "bls_g1_wnaf_mul_batch", "bls_g2_wnaf_mul_batch", "bls_g1_wnaf_mul_window_batch",
+    "bls_g2_wnaf_mul_window_batch", "bls_g1_mul_batch", "bls_g2_mul_batch",
+    "bls_g1_batch_normalization", "bls_g2_batch_normalization", "bls_g1_into_affine_batch",
+    "bls_g2_into_affine_batch", "bls_g1_op_batch", "bls_g2_op_batch", "bls_field_op_batch",
+    "bls_g2_prepare_dev", "bls_miller_loop_dev", "bls_miller_loop_prepared_dev",
+    "bls_final_exponentiation_dev", "bls_pairing_dev", "bls_multi_miller_scratch_bytes",
+    "bls_multi_miller_loop_dev", "bls_fq12_product_scratch_bytes", "bls_fq12_product_dev",
+    "bls_g1_wnaf_mul_dev", "bls_g2_wnaf_mul_dev", "bls_batch_normalization_scratch_bytes",
+    "bls_g1_batch_normalization_dev", "bls_g2_batch_normalization_dev", "bls_imad_peak",
+]
+
+
+class BlsError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BlsError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "or `make -C pairing_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    lib.bls_ctx_create.restype = vp
+    lib.bls_ctx_create.argtypes = [ci, ctypes.POINTER(ci)]
+    lib.bls_ctx_destroy.argtypes = [vp]
+    lib.bls_ctx_destroy.restype = None
+    lib.bls_strerror.restype = ctypes.c_char_p
+    lib.bls_strerror.argtypes = [ci]
+    lib.bls_ctx_last_error.restype = ctypes.c_char_p
+    lib.bls_ctx_last_error.argtypes = [vp]
+    lib.bls_ctx_device.argtypes = [vp]
+    lib.bls_ctx_sm_count.argtypes = [vp]
+    lib.bls_ctx_launch_count.restype = ctypes.c_uint64
+    lib.bls_ctx_launch_count.argtypes = [vp]
+    for name in ("bls_multi_miller_scratch_bytes", "bls_fq12_product_scratch_bytes"):
+        getattr(lib, name).restype = sz
+        getattr(lib, name).argtypes = [vp, sz]
+    lib.bls_batch_normalization_scratch_bytes.restype = sz
+    lib.bls_batch_normalization_scratch_bytes.argtypes = [vp, ci, sz]
+    sig = {
+        "bls_g2_prepare_batch": [vp, vp, vp, sz],
+        "bls_miller_loop_batch": [vp, vp, vp, vp, sz],
+        "bls_miller_loop_prepared_batch": [vp, vp, vp, vp, sz],
+        "bls_multi_miller_loop": [vp, vp, vp, sz, vp],
+        "bls_multi_miller_loop_prepared": [vp, vp, vp, sz, vp],
+        "bls_final_exponentiation_batch": [vp, vp, vp, vp, sz],
+        "bls_pairing_batch": [vp, vp, vp, vp, sz],
+        "bls_fq12_product": [vp, vp, sz, vp],
+        "bls_g1_wnaf_mul_batch": [vp, vp, vp, vp, sz],
+        "bls_g2_wnaf_mul_batch": [vp, vp, vp, vp, sz],
+        "bls_g1_wnaf_mul_window_batch": [vp, vp, vp, vp, sz, ci],
+        "bls_g2_wnaf_mul_window_batch": [vp, vp, vp, vp, sz, ci],
+        "bls_g1_mul_batch": [vp, vp, vp, vp, sz],
+        "bls_g2_mul_batch": [vp, vp, vp, vp, sz],
+        "bls_g1_batch_normalization": [vp, vp, sz],
+        "bls_g2_batch_normalization": [vp, vp, sz],
+        "bls_g1_into_affine_batch": [vp, vp, vp, sz],
+        "bls_g2_into_affine_batch": [vp, vp, vp, sz],
+        "bls_g1_op_batch": [vp, ci, vp, vp, vp, sz],
+        "bls_g2_op_batch": [vp, ci, vp, vp, vp, sz],
+        "bls_field_op_batch": [vp, ci, ci, vp, vp, vp, vp, sz],
+        "bls_g2_prepare_dev": [vp, vp, vp, sz, vp],
+        "bls_miller_loop_dev": [vp, vp, vp, vp, sz, vp],
+        "bls_miller_loop_prepared_dev": [vp, vp, vp, vp, sz, vp],
+        "bls_final_exponentiation_dev": [vp, vp, vp, vp, sz, vp],
+        "bls_pairing_dev": [vp, vp, vp, vp, sz, vp],
+        "bls_multi_miller_loop_dev": [vp, vp, vp, sz, vp, vp, vp],
+        "bls_fq12_product_dev": [vp, vp, sz, vp, vp, vp],
+        "bls_g1_wnaf_mul_dev": [vp, vp, vp, vp, sz, ci, vp],
+        "bls_g2_wnaf_mul_dev": [vp, vp, vp, vp, sz, ci, vp],
+        "bls_g1_batch_normalization_dev": [vp, vp, sz, vp, vp],
+        "bls_g2_batch_normalization_dev": [vp, vp, sz, vp, vp],
+        "bls_imad_peak": [vp, ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = ci
+    _lib = lib
+    return lib
+
+
+def _arr(a, w, name="array"):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.ndim != 2 or a.shape[1] != w:
+        raise ValueError("%s must have shape (n, %d) uint64, got %r" % (name, w, a.shape))
+    return a
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Context:
+    """One CUDA device + stream (bls_ctx).  Host-array methods take and return numpy uint64 arrays
+    in the ABI layouts; `*_dev` methods take raw device pointers (ints) and a CUDA stream handle."""
+
+    def __init__(self, device=0):
+        self._lib = load()
+        err = ctypes.c_int(0)
+        self._ctx = self._lib.bls_ctx_create(int(device), ctypes.byref(err))
+        if not self._ctx:
+            raise BlsError("bls_ctx_create(device=%d) failed: %s" % (device, self._lib.bls_strerror(err.value).decode()))
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.bls_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BlsError("%s [%s]" % (self._lib.bls_strerror(rc).decode(),
+                                        self._lib.bls_ctx_last_error(self._ctx).decode()))
+
+    @property
+    def sm_count(self):
+        return self._lib.bls_ctx_sm_count(self._ctx)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.bls_ctx_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------ engine, host arrays
+    def g2_prepare(self, q):
+        q = _arr(q, W_G2A, "q")
+        out = np.zeros((q.shape[0], W_G2P), dtype=np.uint64)
+        self._check(self._lib.bls_g2_prepare_batch(self._ctx, _p(q), _p(out), q.shape[0]))
+        return out
+
+    def _pq(self, fn, p, q, wq):
+        p, q = _arr(p, W_G1A, "p"), _arr(q, wq, "q")
+        if p.shape[0] != q.shape[0]:
+            raise ValueError("p and q must have the same length")
+        out = np.zeros((p.shape[0], W_FQ12), dtype=np.uint64)
+        self._check(fn(self._ctx, _p(p), _p(q), _p(out), p.shape[0]))
+        return out
+
+    def miller_loop(self, p, q):
+        return self._pq(self._lib.bls_miller_loop_batch, p, q, W_G2A)
+
+    def miller_loop_prepared(self, p, qp):
+        return self._pq(self._lib.bls_miller_loop_prepared_batch, p, qp, W_G2P)
+
+    def pairing(self, p, q):
+        return self._pq(self._lib.bls_pairing_batch, p, q, W_G2A)
+
+    def _multi(self, fn, p, q, wq):
+        p, q = _arr(p, W_G1A, "p"), _arr(q, wq, "q")
+        if p.shape[0] != q.shape[0]:
+            raise ValueError("p and q must have the same length")
+        out = np.zeros((1, W_FQ12), dtype=np.uint64)
+        self._check(fn(self._ctx, _p(p), _p(q), p.shape[0], _p(out)))
+        return out
+
+    def multi_miller_loop(self, p, q):
+        return self._multi(self._lib.bls_multi_miller_loop, p, q, W_G2A)
+
+    def multi_miller_loop_prepared(self, p, qp):
+        return self._multi(self._lib.bls_multi_miller_loop_prepared, p, qp, W_G2P)
+
+    def final_exponentiation(self, f):
+        f = _arr(f, W_FQ12, "f")
+        out = np.zeros_like(f)
+        ok = np.zeros(f.shape[0], dtype=np.uint8)
+        self._check(self._lib.bls_final_exponentiation_batch(self._ctx, _p(f), _p(out), _p(ok), f.shape[0]))
+        return out, ok
+
+    def fq12_product(self, f):
+        f = _arr(f, W_FQ12, "f")
+        out = np.zeros((1, W_FQ12), dtype=np.uint64)
+        self._check(self._lib.bls_fq12_product(self._ctx, _p(f), f.shape[0], _p(out)))
+        return out
+
+    # ------------------------------------------------------------------ curves, host arrays
+    def _wnaf(self, g2, bases, k, window, mode):
+        w = W_G2 if g2 else W_G1
+        bases, k = _arr(bases, w, "bases"), _arr(k, W_FR, "k")
+        if bases.shape[0] != k.shape[0]:
+            raise ValueError("bases and k must have the same length")
+        out = np.zeros_like(bases)
+        n = bases.shape[0]
+        L = self._lib
+        if mode == "mul":
+            fn = L.bls_g2_mul_batch if g2 else L.bls_g1_mul_batch
+            self._check(fn(self._ctx, _p(bases), _p(k), _p(out), n))
+        elif window:
+            fn = L.bls_g2_wnaf_mul_window_batch if g2 else L.bls_g1_wnaf_mul_window_batch
+            self._check(fn(self._ctx, _p(bases), _p(k), _p(out), n, int(window)))
+        else:
+            fn = L.bls_g2_wnaf_mul_batch if g2 else L.bls_g1_wnaf_mul_batch
+            self._check(fn(self._ctx, _p(bases), _p(k), _p(out), n))
+        return out
+
+    def g1_wnaf_mul(self, bases, k, window=0): return self._wnaf(False, bases, k, window, "wnaf")
+    def g2_wnaf_mul(self, bases, k, window=0): return self._wnaf(True, bases, k, window, "wnaf")
+    def g1_mul(self, bases, k): return self._wnaf(False, bases, k, 0, "mul")
+    def g2_mul(self, bases, k): return self._wnaf(True, bases, k, 0, "mul")
+
+    def g1_batch_normalization(self, v):
+        v = _arr(v, W_G1, "v").copy()
+        self._check(self._lib.bls_g1_batch_normalization(self._ctx, _p(v), v.shape[0]))
+        return v
+
+    def g2_batch_normalization(self, v):
+        v = _arr(v, W_G2, "v").copy()
+        self._check(self._lib.bls_g2_batch_normalization(self._ctx, _p(v), v.shape[0]))
+        return v
+
+    def g1_into_affine(self, v):
+        v = _arr(v, W_G1, "v")
+        out = np.zeros((v.shape[0], W_G1A), dtype=np.uint64)
+        self._check(self._lib.bls_g1_into_affine_batch(self._ctx, _p(v), _p(out), v.shape[0]))
+        return out
+
+    def g2_into_affine(self, v):
+        v = _arr(v, W_G2, "v")
+        out = np.zeros((v.shape[0], W_G2A), dtype=np.uint64)
+        self._check(self._lib.bls_g2_into_affine_batch(self._ctx, _p(v), _p(out), v.shape[0]))
+        return out
+
+    def _pt_op(self, g2, op, a, b):
+        w, wa = (W_G2, W_G2A) if g2 else (W_G1, W_G1A)
+        a = _arr(a, w, "a")
+        if b is not None:
+            b = _arr(b, wa if op == "add_mixed" else w, "b")
+        out = np.zeros_like(a)
+        fn = self._lib.bls_g2_op_batch if g2 else self._lib.bls_g1_op_batch
+        self._check(fn(self._ctx, PT_OPS[op], _p(a), _p(b), _p(out), a.shape[0]))
+        return out
+
+    def g1_op(self, op, a, b=None): return self._pt_op(False, op, a, b)
+    def g2_op(self, op, a, b=None): return self._pt_op(True, op, a, b)
+
+    # ------------------------------------------------------------------ field tower, host arrays
+    def field_op(self, degree, op, a, b=None):
+        a = _arr(a, 6 * degree, "a")
+        if b is not None:
+            b = _arr(b, 6 * degree, "b")
+        out = np.zeros_like(a)
+        ok = np.zeros(a.shape[0], dtype=np.uint8)
+        self._check(self._lib.bls_field_op_batch(self._ctx, degree, OPS[op], _p(a), _p(b), _p(out), _p(ok), a.shape[0]))
+        return out, ok
+
+    # ------------------------------------------------------------------ device pointers
+    def call_dev(self, name, *args):
+        """Raw access to a `*_dev` entry point: args are ints (device pointers / sizes / stream)."""
+        self._check(getattr(self._lib, name)(self._ctx, *args))
+
+    def multi_miller_scratch_bytes(self, n):
+        return int(self._lib.bls_multi_miller_scratch_bytes(self._ctx, n))
+
+    def fq12_product_scratch_bytes(self, n):
+        return int(self._lib.bls_fq12_product_scratch_bytes(self._ctx, n))
+
+    def batch_normalization_scratch_bytes(self, degree, n):
+        return int(self._lib.bls_batch_normalization_scratch_bytes(self._ctx, degree, n))
+
+    def imad_peak(self, variant=0, iters=2000):
+        macs, ms = ctypes.c_double(0), ctypes.c_double(0)
+        self._check(self._lib.bls_imad_peak(self._ctx, variant, iters, ctypes.byref(macs), ctypes.byref(ms)))
+        return macs.value, ms.value

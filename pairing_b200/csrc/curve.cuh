@@ -1,0 +1,214 @@
+// curve.cuh -- G1 (over Fq) and G2 (over Fq2) in Jacobian coordinates, wNAF scalar multiplication.
+// One template over the coordinate field, like the reference's `curve_impl!` macro
+// (bls12_381/ec.rs:1-621).  Jacobian (X, Y, Z) triples are representative-dependent, so the formula
+// set, the special cases and the wNAF op sequence follow the reference exactly:
+//   double            dbl-2009-l   ec.rs:296-354
+//   add_assign        add-2007-bl  ec.rs:356-444 (copy when self = inf, no-op when other = inf,
+//                                  double when equal, H = 0 falls through when P + (-P))
+//   add_assign_mixed  madd-2007-bl ec.rs:446-526
+//   wnaf_table / wnaf_form / wnaf_exp   wnaf.rs:4-71
+#pragma once
+#include "tower.cuh"
+
+namespace bls {
+
+// field-generic spellings
+__device__ __forceinline__ Fp f_add(const Fp& a, const Fp& b) { return fp_add(a, b); }
+__device__ __forceinline__ Fp f_sub(const Fp& a, const Fp& b) { return fp_sub(a, b); }
+__device__ __forceinline__ Fp f_dbl(const Fp& a) { return fp_dbl(a); }
+__device__ __forceinline__ Fp f_neg(const Fp& a) { return fp_neg(a); }
+__device__ __forceinline__ Fp f_mul(const Fp& a, const Fp& b) { return fp_mul(a, b); }
+__device__ __forceinline__ Fp f_sqr(const Fp& a) { return fp_sqr(a); }
+__device__ __forceinline__ bool f_is_zero(const Fp& a) { return fp_is_zero(a); }
+__device__ __forceinline__ bool f_eq(const Fp& a, const Fp& b) { return fp_eq(a, b); }
+__device__ __forceinline__ bool f_inv(Fp& r, const Fp& a) { return fp_inv(r, a); }
+__device__ __forceinline__ void f_set_one(Fp& a) { a = fp_one(); }
+__device__ __forceinline__ void f_set_zero(Fp& a) { a = fp_zero(); }
+
+__device__ __forceinline__ Fp2 f_add(const Fp2& a, const Fp2& b) { return fp2_add(a, b); }
+__device__ __forceinline__ Fp2 f_sub(const Fp2& a, const Fp2& b) { return fp2_sub(a, b); }
+__device__ __forceinline__ Fp2 f_dbl(const Fp2& a) { return fp2_dbl(a); }
+__device__ __forceinline__ Fp2 f_neg(const Fp2& a) { return fp2_neg(a); }
+__device__ __forceinline__ Fp2 f_mul(const Fp2& a, const Fp2& b) { return fp2_mul(a, b); }
+__device__ __forceinline__ Fp2 f_sqr(const Fp2& a) { return fp2_sqr(a); }
+__device__ __forceinline__ bool f_is_zero(const Fp2& a) { return fp2_is_zero(a); }
+__device__ __forceinline__ bool f_eq(const Fp2& a, const Fp2& b) { return fp2_eq(a, b); }
+__device__ __forceinline__ bool f_inv(Fp2& r, const Fp2& a) { return fp2_inv(r, a); }
+__device__ __forceinline__ void f_set_one(Fp2& a) { a = fp2_one(); }
+__device__ __forceinline__ void f_set_zero(Fp2& a) { a = fp2_zero(); }
+
+template <class F> struct Jac { F x, y, z; };
+template <class F> struct Aff { F x, y; bool inf; };
+
+template <class F> __device__ __forceinline__ bool pt_is_zero(const Jac<F>& p) { return f_is_zero(p.z); }
+// ec.rs:224-230: (0, 1, 0)
+template <class F> __device__ __forceinline__ void pt_set_zero(Jac<F>& p) { f_set_zero(p.x); f_set_one(p.y); f_set_zero(p.z); }
+template <class F> __device__ __forceinline__ bool pt_is_normalized(const Jac<F>& p) {
+  F one; f_set_one(one);
+  return pt_is_zero(p) || f_eq(p.z, one);
+}
+
+template <class F> __device__ __noinline__ void pt_double(Jac<F>& s) {
+  if (pt_is_zero(s)) return;
+  F a = f_sqr(s.x);
+  F b = f_sqr(s.y);
+  F c = f_sqr(b);
+  F d = f_dbl(f_sub(f_sub(f_sqr(f_add(s.x, b)), a), c));
+  F e = f_add(f_dbl(a), a);
+  F f = f_sqr(e);
+  s.z = f_dbl(f_mul(s.z, s.y));
+  s.x = f_sub(f_sub(f, d), d);
+  c = f_dbl(f_dbl(f_dbl(c)));
+  s.y = f_sub(f_mul(f_sub(d, s.x), e), c);
+}
+
+template <class F> __device__ __noinline__ void pt_add(Jac<F>& s, const Jac<F>& o) {
+  if (pt_is_zero(s)) { s = o; return; }
+  if (pt_is_zero(o)) return;
+  F z1z1 = f_sqr(s.z);
+  F z2z2 = f_sqr(o.z);
+  F u1 = f_mul(s.x, z2z2);
+  F u2 = f_mul(o.x, z1z1);
+  F s1 = f_mul(f_mul(s.y, o.z), z2z2);
+  F s2 = f_mul(f_mul(o.y, s.z), z1z1);
+  if (f_eq(u1, u2) && f_eq(s1, s2)) { pt_double(s); return; }
+  F h = f_sub(u2, u1);
+  F i = f_sqr(f_dbl(h));
+  F j = f_mul(h, i);
+  F r = f_dbl(f_sub(s2, s1));
+  F v = f_mul(u1, i);
+  s.x = f_sub(f_sub(f_sub(f_sqr(r), j), v), v);
+  s.y = f_sub(f_mul(f_sub(v, s.x), r), f_dbl(f_mul(s1, j)));
+  s.z = f_mul(f_sub(f_sub(f_sqr(f_add(s.z, o.z)), z1z1), z2z2), h);
+}
+
+template <class F> __device__ __noinline__ void pt_add_mixed(Jac<F>& s, const Aff<F>& o) {
+  if (o.inf) return;
+  if (pt_is_zero(s)) { s.x = o.x; s.y = o.y; f_set_one(s.z); return; }
+  F z1z1 = f_sqr(s.z);
+  F u2 = f_mul(o.x, z1z1);
+  F s2 = f_mul(f_mul(o.y, s.z), z1z1);
+  if (f_eq(s.x, u2) && f_eq(s.y, s2)) { pt_double(s); return; }
+  F h = f_sub(u2, s.x);
+  F hh = f_sqr(h);
+  F i = f_dbl(f_dbl(hh));
+  F j = f_mul(h, i);
+  F r = f_dbl(f_sub(s2, s.y));
+  F v = f_mul(s.x, i);
+  F x3 = f_sub(f_sub(f_sub(f_sqr(r), j), v), v);
+  F y3 = f_sub(f_mul(f_sub(v, x3), r), f_dbl(f_mul(j, s.y)));
+  s.z = f_sub(f_sub(f_sqr(f_add(s.z, h)), z1z1), hh);
+  s.x = x3; s.y = y3;
+}
+
+// ec.rs:528-532
+template <class F> __device__ __forceinline__ void pt_negate(Jac<F>& s) { if (!pt_is_zero(s)) s.y = f_neg(s.y); }
+
+// ec.rs:586-619 From<projective> for affine
+template <class F> __device__ __noinline__ void pt_into_affine(Aff<F>& out, const Jac<F>& p) {
+  F one; f_set_one(one);
+  if (pt_is_zero(p)) { f_set_zero(out.x); out.y = one; out.inf = true; return; }   // ec.rs:158-164
+  out.inf = false;
+  if (f_eq(p.z, one)) { out.x = p.x; out.y = p.y; return; }
+  F zinv; f_inv(zinv, p.z);
+  F zp = f_sqr(zinv);
+  out.x = f_mul(p.x, zp);
+  out.y = f_mul(p.y, f_mul(zp, zinv));
+}
+
+// ---- scalars (FrRepr, fr.rs:57-244): canonical 256-bit integers, 8 x u32 here ----
+struct Scalar { uint32_t v[8]; };
+
+__device__ __forceinline__ int scalar_num_bits(const Scalar& k) {   // fr.rs:213-225
+  for (int i = 7; i >= 0; i--)
+    if (k.v[i]) return 32 * i + 32 - __clz(k.v[i]);
+  return 0;
+}
+// ec.rs:895-905 / 1586-1596
+__device__ __forceinline__ int g1_window_for_bits(int nb) { return nb >= 130 ? 4 : (nb >= 34 ? 3 : 2); }
+__device__ __forceinline__ int g2_window_for_bits(int nb) { return nb >= 103 ? 4 : (nb >= 37 ? 3 : 2); }
+
+#define BLS_MAX_WNAF_WINDOW 7
+#define BLS_MAX_WNAF_TABLE (1 << (BLS_MAX_WNAF_WINDOW - 1))
+
+// wnaf_form, wnaf.rs:18-43.  Digits are odd in (-2^w, 2^w); |digit| < 128 for w <= 7.
+__device__ __forceinline__ int wnaf_form(int8_t* digits, Scalar c, int window) {
+  int n = 0;
+  const uint32_t mask = (2u << window) - 1u;
+  while (true) {
+    uint32_t nz = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) nz |= c.v[i];
+    if (!nz) break;
+    int u = 0;
+    if (c.v[0] & 1u) {
+      u = (int)(c.v[0] & mask);
+      if (u > (1 << window)) u -= (2 << window);
+      // c -= u  (u may be negative): add the sign-extended negation with carry
+      uint32_t lo = (uint32_t)(-u);
+      uint32_t ext = (u > 0) ? 0xffffffffu : 0u;
+      uint64_t t = (uint64_t)c.v[0] + lo;
+      c.v[0] = (uint32_t)t;
+#pragma unroll
+      for (int i = 1; i < 8; i++) {
+        t = (uint64_t)c.v[i] + ext + (t >> 32);
+        c.v[i] = (uint32_t)t;
+      }
+    }
+    digits[n++] = (int8_t)u;
+#pragma unroll
+    for (int i = 0; i < 7; i++) c.v[i] = (c.v[i] >> 1) | (c.v[i + 1] << 31);
+    c.v[7] >>= 1;
+  }
+  return n;
+}
+
+// Wnaf::new().scalar(k).base(g)  (wnaf.rs:111-128, 158-164) with an explicit window
+template <class F> __device__ __forceinline__ void pt_wnaf_mul(Jac<F>& out, const Jac<F>& base, const Scalar& k, int window,
+                                                          Jac<F>* table, int8_t* digits) {
+  // wnaf_table, wnaf.rs:4-15: table[i] = (2i+1) * base by repeated projective additions of 2*base
+  {
+    Jac<F> b = base, dbl = base;
+    pt_double(dbl);
+    const int tsize = 1 << (window - 1);
+#pragma unroll 1
+    for (int i = 0; i < tsize; i++) { table[i] = b; pt_add(b, dbl); }
+  }
+  int nd = wnaf_form(digits, k, window);
+  // wnaf_exp, wnaf.rs:49-71
+  Jac<F> result;
+  pt_set_zero(result);
+  bool found_one = false;
+#pragma unroll 1
+  for (int i = nd - 1; i >= 0; i--) {
+    int n = digits[i];
+    if (found_one) pt_double(result);
+    if (n != 0) {
+      found_one = true;
+      if (n > 0) {
+        pt_add(result, table[n >> 1]);
+      } else {
+        Jac<F> t = table[(-n) >> 1];     // sub_assign: copy, negate, add (lib.rs:156-160)
+        pt_negate(t);
+        pt_add(result, t);
+      }
+    }
+  }
+  out = result;
+}
+
+// double-and-add, ec.rs:534-553
+template <class F> __device__ __forceinline__ void pt_mul(Jac<F>& s, const Scalar& k) {
+  Jac<F> res;
+  pt_set_zero(res);
+  bool found_one = false;
+#pragma unroll 1
+  for (int n = 255; n >= 0; n--) {
+    bool bit = (k.v[n >> 5] >> (n & 31)) & 1u;
+    if (found_one) pt_double(res); else found_one = bit;
+    if (bit) pt_add(res, s);
+  }
+  s = res;
+}
+
+}  // namespace bls

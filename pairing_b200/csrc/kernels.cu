@@ -1,0 +1,1087 @@
+// kernels.cu -- CUDA kernels (sm_100a) and the C ABI of include/pairing_b200.h.
+//
+// Round-1 mapping: one thread per element (pairing, point, field element); field values live in
+// registers at the Fq/Fq2 level (fp_mul / fp2_mul take and return their operands in registers) and
+// in per-thread local memory (L1-resident, lane-interleaved by the hardware) at the Fq6/Fq12 level.
+// Inputs and outputs use the ABI's array-of-structs layout directly: the path is integer-multiply
+// bound (<= 880 B of HBM traffic per 6.19 M-MAC32 pairing), so HBM layout is
+// not what limits it.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/pairing_b200.h"
+#include "pairing.cuh"
+
+using namespace bls;
+
+// ------------------------------------------------------------------------------------------------
+// ABI <-> register conversions.  ABI structs are arrays of u64 (8-byte aligned).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fp ld_fp(const uint64_t* p) {
+  Fp r;
+  const uint2* q = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+  for (int i = 0; i < 6; i++) { uint2 t = q[i]; r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
+  return r;
+}
+__device__ __forceinline__ void st_fp(uint64_t* p, const Fp& a) {
+  uint2* q = reinterpret_cast<uint2*>(p);
+#pragma unroll
+  for (int i = 0; i < 6; i++) q[i] = make_uint2(a.v[2 * i], a.v[2 * i + 1]);
+}
+__device__ __forceinline__ Fp2 ld_fp2(const uint64_t* p) { return Fp2{ld_fp(p), ld_fp(p + 6)}; }
+__device__ __forceinline__ void st_fp2(uint64_t* p, const Fp2& a) { st_fp(p, a.c0); st_fp(p + 6, a.c1); }
+__device__ __forceinline__ void ld_fp6(Fp6& r, const uint64_t* p) { r.c0 = ld_fp2(p); r.c1 = ld_fp2(p + 12); r.c2 = ld_fp2(p + 24); }
+__device__ __forceinline__ void st_fp6(uint64_t* p, const Fp6& a) { st_fp2(p, a.c0); st_fp2(p + 12, a.c1); st_fp2(p + 24, a.c2); }
+__device__ __forceinline__ void ld_fp12(Fp12& r, const uint64_t* p) { ld_fp6(r.c0, p); ld_fp6(r.c1, p + 36); }
+__device__ __forceinline__ void st_fp12(uint64_t* p, const Fp12& a) { st_fp6(p, a.c0); st_fp6(p + 36, a.c1); }
+
+__device__ __forceinline__ void ld_F(Fp& r, const uint64_t* p) { r = ld_fp(p); }
+__device__ __forceinline__ void ld_F(Fp2& r, const uint64_t* p) { r = ld_fp2(p); }
+__device__ __forceinline__ void st_F(uint64_t* p, const Fp& a) { st_fp(p, a); }
+__device__ __forceinline__ void st_F(uint64_t* p, const Fp2& a) { st_fp2(p, a); }
+template <class F> struct FW;   // words (u64) per coordinate
+template <> struct FW<Fp> { static const int W = 6; };
+template <> struct FW<Fp2> { static const int W = 12; };
+
+template <class F> __device__ __forceinline__ void ld_jac(Jac<F>& r, const uint64_t* p) {
+  ld_F(r.x, p); ld_F(r.y, p + FW<F>::W); ld_F(r.z, p + 2 * FW<F>::W);
+}
+template <class F> __device__ __forceinline__ void st_jac(uint64_t* p, const Jac<F>& a) {
+  st_F(p, a.x); st_F(p + FW<F>::W, a.y); st_F(p + 2 * FW<F>::W, a.z);
+}
+template <class F> __device__ __forceinline__ void ld_aff(Aff<F>& r, const uint64_t* p) {
+  ld_F(r.x, p); ld_F(r.y, p + FW<F>::W); r.inf = p[2 * FW<F>::W] != 0;
+}
+template <class F> __device__ __forceinline__ void st_aff(uint64_t* p, const Aff<F>& a) {
+  st_F(p, a.x); st_F(p + FW<F>::W, a.y); p[2 * FW<F>::W] = a.inf ? 1ull : 0ull;
+}
+__device__ __forceinline__ Scalar ld_scalar(const uint64_t* p) {
+  Scalar s;
+  const uint2* q = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { uint2 t = q[i]; s.v[2 * i] = t.x; s.v[2 * i + 1] = t.y; }
+  return s;
+}
+
+#define G1A_W 13
+#define G1_W 18
+#define G2A_W 25
+#define G2_W 36
+#define FQ12_W 72
+#define G2P_W (68 * 36 + 1)
+
+// ------------------------------------------------------------------------------------------------
+// Field-op kernels (tower parity tests; `Field` trait methods, src/lib.rs:267-325)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fq_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint8_t* ok, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp x = ld_fp(a + 6 * i), y = b ? ld_fp(b + 6 * i) : fp_zero(), r = fp_zero();
+  bool good = true;
+  switch (op) {
+    case BLS_OP_ADD: r = fp_add(x, y); break;
+    case BLS_OP_SUB: r = fp_sub(x, y); break;
+    case BLS_OP_MUL: r = fp_mul(x, y); break;
+    case BLS_OP_SQR: r = fp_sqr(x); break;
+    case BLS_OP_NEG: r = fp_neg(x); break;
+    case BLS_OP_DBL: r = fp_dbl(x); break;
+    case BLS_OP_INV: good = fp_inv(r, x); break;
+    case BLS_OP_FROM_REPR: {   // fq.rs:747-756: valid iff x < q, then x * R2
+      Fp t = x; fp_final_sub(t);
+      good = fp_eq(t, x);
+      r = good ? fp_mul(x, fp_r2()) : fp_zero();
+      break;
+    }
+    case BLS_OP_INTO_REPR: {   // fq.rs:758-777: Montgomery reduction of the padded value == x * 1 * R^-1
+      Fp one = fp_zero(); one.v[0] = 1;
+      r = fp_mul(x, one);
+      break;
+    }
+  }
+  st_fp(out + 6 * i, r);
+  if (ok) ok[i] = good;
+}
+
+__global__ void __launch_bounds__(128) k_fq2_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint8_t* ok, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp2 x = ld_fp2(a + 12 * i), y = b ? ld_fp2(b + 12 * i) : fp2_zero(), r = fp2_zero();
+  bool good = true;
+  switch (op) {
+    case BLS_OP_ADD: r = fp2_add(x, y); break;
+    case BLS_OP_SUB: r = fp2_sub(x, y); break;
+    case BLS_OP_MUL: r = fp2_mul(x, y); break;
+    case BLS_OP_SQR: r = fp2_sqr(x); break;
+    case BLS_OP_NEG: r = fp2_neg(x); break;
+    case BLS_OP_DBL: r = fp2_dbl(x); break;
+    case BLS_OP_INV: good = fp2_inv(r, x); if (!good) r = fp2_zero(); break;
+    case BLS_OP_MUL_NONRES: r = fp2_mul_by_nonresidue(x); break;
+    case BLS_OP_FROB1: r = fp2_frobenius(x, 1); break;
+  }
+  st_fp2(out + 12 * i, r);
+  if (ok) ok[i] = good;
+}
+
+__global__ void __launch_bounds__(128) k_fq6_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint8_t* ok, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp6 x, y, r;
+  ld_fp6(x, a + 36 * i);
+  if (b) ld_fp6(y, b + 36 * i); else y = fp6_zero();
+  r = fp6_zero();
+  bool good = true;
+  switch (op) {
+    case BLS_OP_ADD: fp6_add(r, x, y); break;
+    case BLS_OP_SUB: fp6_sub(r, x, y); break;
+    case BLS_OP_MUL: fp6_mul(r, x, y); break;
+    case BLS_OP_SQR: fp6_sqr(r, x); break;
+    case BLS_OP_NEG: fp6_neg(r, x); break;
+    case BLS_OP_INV: good = fp6_inv(r, x); if (!good) r = fp6_zero(); break;
+    case BLS_OP_MUL_NONRES: fp6_mul_by_nonresidue(r, x); break;
+    case BLS_OP_FROB1: fp6_frobenius(r, x, 1); break;
+    case BLS_OP_FROB2: fp6_frobenius(r, x, 2); break;
+    case BLS_OP_FROB3: fp6_frobenius(r, x, 3); break;
+    case BLS_OP_MUL_BY_01: fp6_mul_by_01(r, x, y.c0, y.c1); break;
+    case BLS_OP_MUL_BY_1: fp6_mul_by_1(r, x, y.c1); break;
+  }
+  st_fp6(out + 36 * i, r);
+  if (ok) ok[i] = good;
+}
+
+__global__ void __launch_bounds__(128) k_fq12_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint8_t* ok, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 x, y, r;
+  ld_fp12(x, a + 72 * i);
+  if (b) ld_fp12(y, b + 72 * i); else { y.c0 = fp6_zero(); y.c1 = fp6_zero(); }
+  r.c0 = fp6_zero(); r.c1 = fp6_zero();
+  bool good = true;
+  switch (op) {
+    case BLS_OP_MUL: fp12_mul(r, x, y); break;
+    case BLS_OP_SQR: fp12_sqr(r, x); break;
+    case BLS_OP_INV: good = fp12_inv(r, x); if (!good) { r.c0 = fp6_zero(); r.c1 = fp6_zero(); } break;
+    case BLS_OP_CONJ: r = x; fp12_conjugate(r); break;
+    case BLS_OP_FROB1: fp12_frobenius(r, x, 1); break;
+    case BLS_OP_FROB2: fp12_frobenius(r, x, 2); break;
+    case BLS_OP_FROB3: fp12_frobenius(r, x, 3); break;
+    case BLS_OP_MUL_BY_014: r = x; fp12_mul_by_014(r, y.c0.c0, y.c0.c1, y.c1.c1); break;
+  }
+  st_fp12(out + 72 * i, r);
+  if (ok) ok[i] = good;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pairing kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_coeffs(uint64_t* p, const Coeffs& c) { st_fp2(p, c.c0); st_fp2(p + 12, c.c1); st_fp2(p + 24, c.c2); }
+__device__ __forceinline__ void ld_coeffs(Coeffs& c, const uint64_t* p) { c.c0 = ld_fp2(p); c.c1 = ld_fp2(p + 12); c.c2 = ld_fp2(p + 24); }
+
+// G2Prepared::from_affine, mod.rs:168-358
+__global__ void __launch_bounds__(128) k_g2_prepare(const uint64_t* q, uint64_t* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t* qi = q + G2A_W * i;
+  uint64_t* o = out + (size_t)G2P_W * i;
+  if (qi[24] != 0) {   // infinity: empty coefficient list + flag (mod.rs:169-174); zero-fill the slots
+    for (int w = 0; w < G2P_W - 1; w++) o[w] = 0;
+    o[G2P_W - 1] = 1;
+    return;
+  }
+  Fp2 qx = ld_fp2(qi), qy = ld_fp2(qi + 12);
+  Jac<Fp2> r; r.x = qx; r.y = qy; r.z = fp2_one();
+  Coeffs c;
+  int idx = 0;
+#pragma unroll 1
+  for (int b = BLS_LOOP_TOP; b >= 0; b--) {
+    g2_doubling_step(r, c);
+    st_coeffs(o + 36 * idx, c); idx++;
+    if ((BLS_LOOP_BITS >> b) & 1ull) {
+      g2_addition_step(r, qx, qy, c);
+      st_coeffs(o + 36 * idx, c); idx++;
+    }
+  }
+  g2_doubling_step(r, c);
+  st_coeffs(o + 36 * idx, c);
+  o[G2P_W - 1] = 0;
+}
+
+// n independent single-pair Miller loops (+ optional final exponentiation = Engine::pairing)
+template <bool FINAL_EXP>
+__global__ void __launch_bounds__(128) k_miller(const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t* pi = p + G1A_W * i;
+  const uint64_t* qi = q + G2A_W * i;
+  bool live = pi[12] == 0 && qi[24] == 0;
+  Fp px = ld_fp(pi), py = ld_fp(pi + 6);
+  Fp2 qx = ld_fp2(qi), qy = ld_fp2(qi + 12);
+  Fp12 f;
+  miller_loop_single(f, px, py, qx, qy, live);
+  if (FINAL_EXP) {
+    Fp12 g;
+    final_exponentiation(g, f);   // Miller values of valid points are non-zero (lib.rs:108 unwrap)
+    st_fp12(out + FQ12_W * i, g);
+  } else {
+    st_fp12(out + FQ12_W * i, f);
+  }
+}
+
+// Miller loop from stored coefficients, the reference's literal miller_loop (mod.rs:40-102), one pair
+__device__ __forceinline__ void miller_loop_prepared_single(Fp12& f, const Fp& px, const Fp& py, const uint64_t* coeffs, bool live) {
+  fp12_one(f);
+  if (!live) return;
+  Coeffs c;
+  int idx = 0;
+#pragma unroll 1
+  for (int b = BLS_LOOP_TOP; b >= 0; b--) {
+    ld_coeffs(c, coeffs + 36 * idx); idx++;
+    ell(f, c, px, py);
+    if ((BLS_LOOP_BITS >> b) & 1ull) {
+      ld_coeffs(c, coeffs + 36 * idx); idx++;
+      ell(f, c, px, py);
+    }
+    fp12_sqr(f, f);
+  }
+  ld_coeffs(c, coeffs + 36 * idx);
+  ell(f, c, px, py);
+  fp12_conjugate(f);
+}
+
+__global__ void __launch_bounds__(128) k_miller_prepared(const uint64_t* p, const uint64_t* qp, uint64_t* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t* pi = p + G1A_W * i;
+  const uint64_t* qi = qp + (size_t)G2P_W * i;
+  bool live = pi[12] == 0 && qi[G2P_W - 1] == 0;
+  Fp px = ld_fp(pi), py = ld_fp(pi + 6);
+  Fp12 f;
+  miller_loop_prepared_single(f, px, py, qi, live);
+  st_fp12(out + FQ12_W * i, f);
+}
+
+__global__ void __launch_bounds__(128) k_final_exp(const uint64_t* in, uint64_t* out, uint8_t* is_some, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp12 f, g;
+  ld_fp12(f, in + FQ12_W * i);
+  bool ok = final_exponentiation(g, f);
+  st_fp12(out + FQ12_W * i, g);
+  if (is_some) is_some[i] = ok;
+}
+
+// Multi-pairing Miller loop (mod.rs:80-95): thread t owns pairs t, t+T, t+2T, ... and ONE accumulator
+// f shared by all of them, so the 62 Fq12 squarings are paid once per thread, not once per pair.
+// The running G2 points R_j live in a lane-interleaved scratch array (word-major, pair-minor) so that
+// a warp's loads/stores of one word are contiguous.  Each thread emits one partial product.
+__device__ __forceinline__ void ld_jac2_soa(Jac<Fp2>& r, const uint32_t* s, size_t n, size_t pair) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+#pragma unroll
+  for (int k = 0; k < 72; k++) w[k] = s[(size_t)k * n + pair];
+}
+__device__ __forceinline__ void st_jac2_soa(uint32_t* s, size_t n, size_t pair, const Jac<Fp2>& r) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
+#pragma unroll
+  for (int k = 0; k < 72; k++) s[(size_t)k * n + pair] = w[k];
+}
+
+__global__ void __launch_bounds__(128) k_multi_miller(const uint64_t* p, const uint64_t* q, size_t n, uint32_t* rstate, uint64_t* partials) {
+  const size_t T = (size_t)gridDim.x * blockDim.x;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Fp12 f;
+  fp12_one(f);
+  Coeffs c;
+  Jac<Fp2> r;
+#pragma unroll 1
+  for (int b = BLS_LOOP_TOP; b >= -1; b--) {   // b == -1 is the trailing doubling step (mod.rs:92-94)
+    const bool bit = b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull);
+#pragma unroll 1
+    for (size_t i = t; i < n; i += T) {
+      const uint64_t* pi = p + G1A_W * i;
+      const uint64_t* qi = q + G2A_W * i;
+      if (pi[12] != 0 || qi[24] != 0) continue;   // pairs with an infinity member are skipped, mod.rs:49-54
+      if (b == BLS_LOOP_TOP) { r.x = ld_fp2(qi); r.y = ld_fp2(qi + 12); r.z = fp2_one(); }
+      else ld_jac2_soa(r, rstate, n, i);
+      g2_doubling_step(r, c);
+      ell(f, c, ld_fp(pi), ld_fp(pi + 6));
+      if (b >= 0) st_jac2_soa(rstate, n, i, r);
+    }
+    if (bit) {
+#pragma unroll 1
+      for (size_t i = t; i < n; i += T) {
+        const uint64_t* pi = p + G1A_W * i;
+        const uint64_t* qi = q + G2A_W * i;
+        if (pi[12] != 0 || qi[24] != 0) continue;
+        ld_jac2_soa(r, rstate, n, i);
+        g2_addition_step(r, ld_fp2(qi), ld_fp2(qi + 12), c);
+        ell(f, c, ld_fp(pi), ld_fp(pi + 6));
+        st_jac2_soa(rstate, n, i, r);
+      }
+    }
+    if (b >= 0) fp12_sqr(f, f);
+  }
+  fp12_conjugate(f);
+  st_fp12(partials + FQ12_W * t, f);
+}
+
+__global__ void __launch_bounds__(128) k_multi_miller_prepared(const uint64_t* p, const uint64_t* qp, size_t n, uint64_t* partials) {
+  const size_t T = (size_t)gridDim.x * blockDim.x;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  Fp12 f;
+  fp12_one(f);
+  Coeffs c;
+  int idx = 0;
+#pragma unroll 1
+  for (int b = BLS_LOOP_TOP; b >= -1; b--) {
+    const bool bit = b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull);
+    for (int rep = 0; rep < (bit ? 2 : 1); rep++) {
+#pragma unroll 1
+      for (size_t i = t; i < n; i += T) {
+        const uint64_t* pi = p + G1A_W * i;
+        const uint64_t* qi = qp + (size_t)G2P_W * i;
+        if (pi[12] != 0 || qi[G2P_W - 1] != 0) continue;
+        ld_coeffs(c, qi + 36 * idx);
+        ell(f, c, ld_fp(pi), ld_fp(pi + 6));
+      }
+      idx++;
+    }
+    if (b >= 0) fp12_sqr(f, f);
+  }
+  fp12_conjugate(f);
+  st_fp12(partials + FQ12_W * t, f);
+}
+
+// Product of `count` Fq12 values: each of T threads multiplies a strided subset of <= 8 factors; the
+// host repeats the pass (count -> ceil(count/8)) until one value is left.
+__global__ void __launch_bounds__(128) k_fq12_product(const uint64_t* in, size_t count, uint64_t* out, size_t T) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  Fp12 acc, x;
+  fp12_one(acc);
+#pragma unroll 1
+  for (size_t i = t; i < count; i += T) {
+    ld_fp12(x, in + FQ12_W * i);
+    fp12_mul(acc, acc, x);
+  }
+  st_fp12(out + FQ12_W * t, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Curve kernels
+// ------------------------------------------------------------------------------------------------
+template <class F, bool IS_G2, int MAXT>
+__global__ void __launch_bounds__(128) k_wnaf_mul(const uint64_t* bases, const uint64_t* k, uint64_t* out, size_t n, int window) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int PW = 3 * FW<F>::W;
+  Jac<F> base, res;
+  ld_jac(base, bases + (size_t)PW * i);
+  Scalar s = ld_scalar(k + 4 * i);
+  int w = window;
+  if (w == 0) {
+    int nb = scalar_num_bits(s);
+    w = IS_G2 ? g2_window_for_bits(nb) : g1_window_for_bits(nb);
+  }
+  Jac<F> table[MAXT];   // 2^(w-1) entries: 8 covers the per-scalar heuristics (w <= 4)
+  int8_t digits[260];
+  pt_wnaf_mul(res, base, s, w, table, digits);
+  st_jac(out + (size_t)PW * i, res);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_pt_mul(const uint64_t* bases, const uint64_t* k, uint64_t* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int PW = 3 * FW<F>::W;
+  Jac<F> base;
+  ld_jac(base, bases + (size_t)PW * i);
+  Scalar s = ld_scalar(k + 4 * i);
+  pt_mul(base, s);
+  st_jac(out + (size_t)PW * i, base);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_pt_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int PW = 3 * FW<F>::W, AW = 2 * FW<F>::W + 1;
+  Jac<F> x, y;
+  ld_jac(x, a + (size_t)PW * i);
+  switch (op) {
+    case BLS_PT_DOUBLE: pt_double(x); break;
+    case BLS_PT_ADD: ld_jac(y, b + (size_t)PW * i); pt_add(x, y); break;
+    case BLS_PT_SUB: ld_jac(y, b + (size_t)PW * i); pt_negate(y); pt_add(x, y); break;
+    case BLS_PT_ADD_MIXED: { Aff<F> o; ld_aff(o, b + (size_t)AW * i); pt_add_mixed(x, o); break; }
+    case BLS_PT_NEGATE: pt_negate(x); break;
+  }
+  st_jac(out + (size_t)PW * i, x);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_into_affine(const uint64_t* in, uint64_t* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int PW = 3 * FW<F>::W, AW = 2 * FW<F>::W + 1;
+  Jac<F> x;
+  Aff<F> o;
+  ld_jac(x, in + (size_t)PW * i);
+  pt_into_affine(o, x);
+  st_aff(out + (size_t)AW * i, o);
+}
+
+// CurveProjective::batch_normalization (ec.rs:246-294).  The reference runs Montgomery's trick over
+// the whole slice with one inversion; the outputs (x/z^2, y/z^3, one) are canonical field values, so
+// any partition of the trick gives the same bits.  Here thread t owns points t, t+T, ... : a forward
+// pass of prefix products of z (kept in `scratch`, one coordinate per point), one inversion per
+// thread, and a backward pass that yields 1/z and applies the affine map at once.
+template <class F>
+__global__ void __launch_bounds__(128) k_batch_normalization(uint64_t* pts, size_t n, uint64_t* scratch) {
+  const size_t T = (size_t)gridDim.x * blockDim.x;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int W = FW<F>::W, PW = 3 * W;
+  F one; f_set_one(one);
+  F acc = one;
+  size_t last = t;
+  bool any = false;
+#pragma unroll 1
+  for (size_t i = t; i < n; i += T) {
+    F z; ld_F(z, pts + (size_t)PW * i + 2 * W);
+    last = i;
+    if (f_is_zero(z) || f_eq(z, one)) continue;   // is_normalized, ec.rs:242-244
+    st_F(scratch + (size_t)W * i, acc);           // product of the previous live z's
+    acc = f_mul(acc, z);
+    any = true;
+  }
+  if (!any) return;
+  F inv; f_inv(inv, acc);
+#pragma unroll 1
+  for (size_t i = last;; i -= T) {
+    uint64_t* pi = pts + (size_t)PW * i;
+    F z; ld_F(z, pi + 2 * W);
+    if (!(f_is_zero(z) || f_eq(z, one))) {
+      F prev; ld_F(prev, scratch + (size_t)W * i);
+      F zinv = f_mul(inv, prev);
+      inv = f_mul(inv, z);
+      F zz = f_sqr(zinv);
+      F x, y; ld_F(x, pi); ld_F(y, pi + W);
+      st_F(pi, f_mul(x, zz));
+      st_F(pi + W, f_mul(y, f_mul(zz, zinv)));
+      st_F(pi + 2 * W, one);
+    }
+    if (i < T + t) break;   // i == t was the first point of this thread
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Integer-multiply peak microbenchmarks (roofline denominator)
+// ------------------------------------------------------------------------------------------------
+#define PEAK_CHAINS 8
+#define PEAK_UNROLL 32
+__global__ void __launch_bounds__(256) k_imad_wide_peak(uint32_t seed, int iters, uint64_t* sink) {
+  uint64_t acc[PEAK_CHAINS];
+  uint32_t a[PEAK_CHAINS];
+  uint32_t b = seed ^ (threadIdx.x * 2654435761u);
+#pragma unroll
+  for (int k = 0; k < PEAK_CHAINS; k++) { acc[k] = seed + k; a[k] = b * (k + 3) + 1; }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < PEAK_UNROLL; u++) {
+#pragma unroll
+      for (int k = 0; k < PEAK_CHAINS; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a[k]), "r"(b));
+    }
+  }
+  uint64_t s = 0;
+#pragma unroll
+  for (int k = 0; k < PEAK_CHAINS; k++) s ^= acc[k];
+  if (s == 0x1234567ull) sink[0] = s;
+}
+__global__ void __launch_bounds__(256) k_imad32_peak(uint32_t seed, int iters, uint64_t* sink) {
+  uint32_t acc[PEAK_CHAINS];
+  uint32_t a[PEAK_CHAINS];
+  uint32_t b = seed ^ (threadIdx.x * 2654435761u);
+#pragma unroll
+  for (int k = 0; k < PEAK_CHAINS; k++) { acc[k] = seed + k; a[k] = b * (k + 3) + 1; }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < PEAK_UNROLL; u++) {
+#pragma unroll
+      for (int k = 0; k < PEAK_CHAINS; k++) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc[k]) : "r"(a[k]), "r"(b));
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < PEAK_CHAINS; k++) s ^= acc[k];
+  if (s == 0x1234567u) sink[0] = s;
+}
+// the shape fp_mul issues: carry-linked IMAD.WIDE.U32.X rows; 300 MAC32 per fp_mul
+__global__ void __launch_bounds__(256) k_fpmul_peak(uint32_t seed, int iters, uint64_t* sink) {
+  Fp x = fp_one(), y = fp_r2();
+  x.v[0] ^= seed ^ threadIdx.x;
+  y.v[1] ^= seed;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    x = fp_mul_inline(x, y);
+    y = fp_mul_inline(y, x);
+  }
+  if (x.v[0] == 0x1234567u && y.v[3] == 7u) sink[0] = x.v[1];
+}
+
+// carry-linked rows only: 2 x (12-word mad.lo.cc/madc.hi.cc chain) per step, no reduction, no adds
+__global__ void __launch_bounds__(256) k_carry_row_peak(uint32_t seed, int iters, uint64_t* sink) {
+  uint32_t e[12], o[12], x[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) { e[k] = seed + k; o[k] = seed * 3 + k; x[k] = (seed ^ threadIdx.x) * (2 * k + 1) + 1; }
+  uint32_t b = seed ^ (threadIdx.x * 2654435761u);
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      fp_cmad_row(e, &x[0], b, o[11]);
+      fp_cmad_row(o, &x[1], b, e[11]);
+    }
+  }
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < 12; k++) s ^= e[k] ^ o[k];
+  if (s == 0x1234567u) sink[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side: context + C ABI
+// ------------------------------------------------------------------------------------------------
+struct bls_ctx {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  uint64_t launches;
+  char last_error[256];
+};
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      snprintf(ctx->last_error, sizeof(ctx->last_error), "%s: %s", #call, cudaGetErrorString(e_)); \
+      return e_ == cudaErrorMemoryAllocation ? BLS_ERR_OUT_OF_MEMORY : BLS_ERR_CUDA;  \
+    }                                                                                 \
+  } while (0)
+
+static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+static const int TPB = 128;
+
+extern "C" {
+
+bls_ctx* bls_ctx_create(int device, int* err) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) { if (err) *err = BLS_ERR_NO_DEVICE; return nullptr; }
+  if (device < 0 || device >= count) { if (err) *err = BLS_ERR_INVALID_ARGUMENT; return nullptr; }
+  bls_ctx* ctx = new (std::nothrow) bls_ctx();
+  if (!ctx) { if (err) *err = BLS_ERR_OUT_OF_MEMORY; return nullptr; }
+  ctx->device = device;
+  ctx->launches = 0;
+  ctx->last_error[0] = 0;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    if (err) *err = BLS_ERR_CUDA;
+    delete ctx;
+    return nullptr;
+  }
+  if (err) *err = BLS_OK;
+  return ctx;
+}
+
+void bls_ctx_destroy(bls_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* bls_strerror(int status) {
+  switch (status) {
+    case BLS_OK: return "ok";
+    case BLS_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case BLS_ERR_NO_DEVICE: return "no CUDA device (there is no CPU fallback)";
+    case BLS_ERR_CUDA: return "CUDA error (see bls_ctx_last_error)";
+    case BLS_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case BLS_ERR_UNSUPPORTED: return "unsupported";
+  }
+  return "unknown status";
+}
+const char* bls_ctx_last_error(const bls_ctx* ctx) { return ctx ? ctx->last_error : ""; }
+int bls_ctx_device(const bls_ctx* ctx) { return ctx ? ctx->device : -1; }
+int bls_ctx_sm_count(const bls_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+uint64_t bls_ctx_launch_count(const bls_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+static inline cudaStream_t pick(bls_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+#define LAUNCH_CHECK()                                  \
+  do {                                                  \
+    ctx->launches++;                                    \
+    CK(cudaGetLastError());                             \
+  } while (0)
+
+// ---- device-pointer entry points --------------------------------------------------------------
+extern "C" {
+
+int bls_g2_prepare_dev(bls_ctx* ctx, const bls_g2_affine* q, bls_g2_prepared* out, size_t n, void* stream) {
+  if (!ctx || (n && (!q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_g2_prepare<<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)q, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream) {
+  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_miller<false><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_miller_loop_prepared_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q, bls_fq12* out, size_t n, void* stream) {
+  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_miller_prepared<<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_final_exponentiation_dev(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n, void* stream) {
+  if (!ctx || (n && (!in || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_final_exp<<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)in, (uint64_t*)out, is_some, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_pairing_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream) {
+  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_miller<true><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+
+// threads used by the multi-Miller kernel for n pairs: enough pairs per thread to amortise the
+// shared squarings, but never more threads than pairs
+static size_t mm_threads(const bls_ctx* ctx, size_t n) {
+  size_t full = (size_t)ctx->sm_count * 2 * TPB;   // 2 blocks of 128 per SM
+  size_t t = n < full ? n : full;
+  t = (t + TPB - 1) / TPB * TPB;
+  return t ? t : TPB;
+}
+// product tree: a pass over `count` factors uses ceil(count/8) threads
+static size_t prod_threads(size_t count) { return count ? (count + 7) / 8 : 1; }
+size_t bls_fq12_product_scratch_bytes(const bls_ctx* ctx, size_t n) {
+  (void)ctx;
+  return 2 * prod_threads(n) * sizeof(bls_fq12);
+}
+size_t bls_multi_miller_scratch_bytes(const bls_ctx* ctx, size_t n) {
+  if (!ctx) return 0;
+  size_t T = mm_threads(ctx, n);
+  return n * 72 * sizeof(uint32_t) + T * sizeof(bls_fq12) + bls_fq12_product_scratch_bytes(ctx, T);
+}
+
+static int product_passes(bls_ctx* ctx, const uint64_t* in, size_t count, bls_fq12* out1, uint64_t* scratch, cudaStream_t s) {
+  // scratch holds two ping-pong arrays of prod_threads(count) Fq12 each
+  const size_t cap = prod_threads(count);
+  uint64_t* bufs[2] = {scratch, scratch + cap * FQ12_W};
+  int which = 0;
+  const uint64_t* src = in;
+  while (true) {
+    size_t T = prod_threads(count);
+    uint64_t* dst = T == 1 ? (uint64_t*)out1 : bufs[which];
+    k_fq12_product<<<blocks_for(T, TPB), TPB, 0, s>>>(src, count, dst, T);
+    LAUNCH_CHECK();
+    if (T == 1) return BLS_OK;
+    src = dst;
+    count = T;
+    which ^= 1;
+  }
+}
+
+int bls_fq12_product_dev(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq12* out1, void* scratch, void* stream) {
+  if (!ctx || !out1 || (n && (!in || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = pick(ctx, stream);
+  if (n == 0) {   // empty product = one
+    k_fq12_product<<<1, TPB, 0, s>>>((const uint64_t*)in, 0, (uint64_t*)out1, 1);
+    LAUNCH_CHECK();
+    return BLS_OK;
+  }
+  return product_passes(ctx, (const uint64_t*)in, n, out1, (uint64_t*)scratch, s);
+}
+
+int bls_multi_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, void* scratch, void* stream) {
+  if (!ctx || !out1 || (n && (!p || !q || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = pick(ctx, stream);
+  if (n == 0) {
+    k_fq12_product<<<1, TPB, 0, s>>>(nullptr, 0, (uint64_t*)out1, 1);
+    LAUNCH_CHECK();
+    return BLS_OK;
+  }
+  size_t T = mm_threads(ctx, n);
+  uint32_t* rstate = (uint32_t*)scratch;
+  uint64_t* partials = (uint64_t*)((char*)scratch + n * 72 * sizeof(uint32_t));
+  uint64_t* prod_scratch = partials + T * FQ12_W;
+  k_multi_miller<<<(unsigned)(T / TPB), TPB, 0, s>>>((const uint64_t*)p, (const uint64_t*)q, n, rstate, partials);
+  LAUNCH_CHECK();
+  return product_passes(ctx, partials, T, out1, prod_scratch, s);
+}
+
+int bls_g1_wnaf_mul_dev(bls_ctx* ctx, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n, int window, void* stream) {
+  if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  if (window <= 4) k_wnaf_mul<Fp, false, 8><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  else k_wnaf_mul<Fp, false, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_g2_wnaf_mul_dev(bls_ctx* ctx, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n, int window, void* stream) {
+  if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  if (window <= 4) k_wnaf_mul<Fp2, true, 8><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  else k_wnaf_mul<Fp2, true, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+
+// threads for batch normalisation: >= 64 points per thread when n allows it
+static size_t bn_threads(const bls_ctx* ctx, size_t n) {
+  size_t t = (n + 63) / 64;
+  size_t cap = (size_t)ctx->sm_count * 8 * TPB;
+  if (t > cap) t = cap;
+  t = (t + TPB - 1) / TPB * TPB;
+  return t ? t : TPB;
+}
+size_t bls_batch_normalization_scratch_bytes(const bls_ctx* ctx, int degree, size_t n) {
+  (void)ctx;
+  return n * (degree == 2 ? sizeof(bls_fq2) : sizeof(bls_fq));
+}
+int bls_g1_batch_normalization_dev(bls_ctx* ctx, bls_g1* inout, size_t n, void* scratch, void* stream) {
+  if (!ctx || (n && (!inout || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  size_t T = bn_threads(ctx, n);
+  k_batch_normalization<Fp><<<(unsigned)(T / TPB), TPB, 0, pick(ctx, stream)>>>((uint64_t*)inout, n, (uint64_t*)scratch);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_g2_batch_normalization_dev(bls_ctx* ctx, bls_g2* inout, size_t n, void* scratch, void* stream) {
+  if (!ctx || (n && (!inout || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  size_t T = bn_threads(ctx, n);
+  k_batch_normalization<Fp2><<<(unsigned)(T / TPB), TPB, 0, pick(ctx, stream)>>>((uint64_t*)inout, n, (uint64_t*)scratch);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+
+}  // extern "C"
+
+// ---- host-pointer entry points: stage through stream-ordered device buffers -----------------------
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  cudaStream_t s;
+  explicit DevBuf(cudaStream_t s_) : s(s_) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
+  ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+};
+}  // namespace
+
+#define H2D(buf, host, bytes)                                                          \
+  DevBuf buf(ctx->stream);                                                             \
+  CK(buf.alloc(bytes));                                                                \
+  if (host) CK(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream))
+#define DALLOC(buf, bytes) \
+  DevBuf buf(ctx->stream); \
+  CK(buf.alloc(bytes))
+#define D2H(host, buf, bytes) CK(cudaMemcpyAsync(host, buf.p, bytes, cudaMemcpyDeviceToHost, ctx->stream))
+#define SYNC() CK(cudaStreamSynchronize(ctx->stream))
+#define TRY(call)            \
+  do {                       \
+    int rc_ = (call);        \
+    if (rc_ != BLS_OK) return rc_; \
+  } while (0)
+
+extern "C" {
+
+int bls_g2_prepare_batch(bls_ctx* ctx, const bls_g2_affine* q, bls_g2_prepared* out, size_t n) {
+  if (!ctx || (n && (!q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  H2D(dq, q, n * sizeof(*q));
+  DALLOC(dout, n * sizeof(*out));
+  TRY(bls_g2_prepare_dev(ctx, (const bls_g2_affine*)dq.p, (bls_g2_prepared*)dout.p, n, nullptr));
+  D2H(out, dout, n * sizeof(*out));
+  SYNC();
+  return BLS_OK;
+}
+
+static int miller_like(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, bool final_exp) {
+  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  H2D(dp, p, n * sizeof(*p));
+  H2D(dq, q, n * sizeof(*q));
+  DALLOC(dout, n * sizeof(*out));
+  if (final_exp) TRY(bls_pairing_dev(ctx, (const bls_g1_affine*)dp.p, (const bls_g2_affine*)dq.p, (bls_fq12*)dout.p, n, nullptr));
+  else TRY(bls_miller_loop_dev(ctx, (const bls_g1_affine*)dp.p, (const bls_g2_affine*)dq.p, (bls_fq12*)dout.p, n, nullptr));
+  D2H(out, dout, n * sizeof(*out));
+  SYNC();
+  return BLS_OK;
+}
+int bls_miller_loop_batch(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n) { return miller_like(ctx, p, q, out, n, false); }
+int bls_pairing_batch(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n) { return miller_like(ctx, p, q, out, n, true); }
+
+int bls_miller_loop_prepared_batch(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q, bls_fq12* out, size_t n) {
+  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  H2D(dp, p, n * sizeof(*p));
+  H2D(dq, q, n * sizeof(*q));
+  DALLOC(dout, n * sizeof(*out));
+  TRY(bls_miller_loop_prepared_dev(ctx, (const bls_g1_affine*)dp.p, (const bls_g2_prepared*)dq.p, (bls_fq12*)dout.p, n, nullptr));
+  D2H(out, dout, n * sizeof(*out));
+  SYNC();
+  return BLS_OK;
+}
+
+int bls_multi_miller_loop(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1) {
+  if (!ctx || !out1 || (n && (!p || !q))) return BLS_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  H2D(dp, p, n * sizeof(*p));
+  H2D(dq, q, n * sizeof(*q));
+  DALLOC(dscr, bls_multi_miller_scratch_bytes(ctx, n));
+  DALLOC(dout, sizeof(*out1));
+  TRY(bls_multi_miller_loop_dev(ctx, (const bls_g1_affine*)dp.p, (const bls_g2_affine*)dq.p, n, (bls_fq12*)dout.p, dscr.p, nullptr));
+  D2H(out1, dout, sizeof(*out1));
+  SYNC();
+  return BLS_OK;
+}
+
+int bls_multi_miller_loop_prepared(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q, size_t n, bls_fq12* out1) {
+  if (!ctx || !out1 || (n && (!p || !q))) return BLS_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  H2D(dp, p, n * sizeof(*p));
+  H2D(dq, q, n * sizeof(*q));
+  size_t T = mm_threads(ctx, n);
+  DALLOC(dpart, T * sizeof(bls_fq12));
+  DALLOC(dscr, bls_fq12_product_scratch_bytes(ctx, T));
+  DALLOC(dout, sizeof(*out1));
+  k_multi_miller_prepared<<<(unsigned)(T / TPB), TPB, 0, ctx->stream>>>((const uint64_t*)dp.p, (const uint64_t*)dq.p, n, (uint64_t*)dpart.p);
+  LAUNCH_CHECK();
+  TRY(product_passes(ctx, (const uint64_t*)dpart.p, T, (bls_fq12*)dout.p, (uint64_t*)dscr.p, ctx->stream));
+  D2H(out1, dout, sizeof(*out1));
+  SYNC();
+  return BLS_OK;
+}
+
+int bls_final_exponentiation_batch(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n) {
+  if (!ctx || (n && (!in || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  H2D(din, in, n * sizeof(*in));
+  DALLOC(dout, n * sizeof(*out));
+  DALLOC(dok, n);
+  TRY(bls_final_exponentiation_dev(ctx, (const bls_fq12*)din.p, (bls_fq12*)dout.p, (uint8_t*)dok.p, n, nullptr));
+  D2H(out, dout, n * sizeof(*out));
+  if (is_some) D2H(is_some, dok, n);
+  SYNC();
+  return BLS_OK;
+}
+
+int bls_fq12_product(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq12* out1) {
+  if (!ctx || !out1 || (n && !in)) return BLS_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  H2D(din, in, n * sizeof(*in));
+  DALLOC(dscr, bls_fq12_product_scratch_bytes(ctx, n));
+  DALLOC(dout, sizeof(*out1));
+  TRY(bls_fq12_product_dev(ctx, (const bls_fq12*)din.p, n, (bls_fq12*)dout.p, dscr.p, nullptr));
+  D2H(out1, dout, sizeof(*out1));
+  SYNC();
+  return BLS_OK;
+}
+
+static int wnaf_host(bls_ctx* ctx, int degree, const void* bases, const bls_fr_repr* k, void* out, size_t n, int window, int mode) {
+  if (!ctx || (n && (!bases || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
+  H2D(db, bases, n * pb);
+  H2D(dk, k, n * sizeof(*k));
+  DALLOC(dout, n * pb);
+  if (mode == 0) {
+    if (degree == 2) TRY(bls_g2_wnaf_mul_dev(ctx, (const bls_g2*)db.p, (const bls_fr_repr*)dk.p, (bls_g2*)dout.p, n, window, nullptr));
+    else TRY(bls_g1_wnaf_mul_dev(ctx, (const bls_g1*)db.p, (const bls_fr_repr*)dk.p, (bls_g1*)dout.p, n, window, nullptr));
+  } else {
+    if (degree == 2) k_pt_mul<Fp2><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)db.p, (const uint64_t*)dk.p, (uint64_t*)dout.p, n);
+    else k_pt_mul<Fp><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)db.p, (const uint64_t*)dk.p, (uint64_t*)dout.p, n);
+    LAUNCH_CHECK();
+  }
+  D2H(out, dout, n * pb);
+  SYNC();
+  return BLS_OK;
+}
+int bls_g1_wnaf_mul_batch(bls_ctx* ctx, const bls_g1* b, const bls_fr_repr* k, bls_g1* out, size_t n) { return wnaf_host(ctx, 1, b, k, out, n, 0, 0); }
+int bls_g2_wnaf_mul_batch(bls_ctx* ctx, const bls_g2* b, const bls_fr_repr* k, bls_g2* out, size_t n) { return wnaf_host(ctx, 2, b, k, out, n, 0, 0); }
+int bls_g1_wnaf_mul_window_batch(bls_ctx* ctx, const bls_g1* b, const bls_fr_repr* k, bls_g1* out, size_t n, int window) {
+  if (window < 2 || window > BLS_MAX_WNAF_WINDOW) return BLS_ERR_INVALID_ARGUMENT;
+  return wnaf_host(ctx, 1, b, k, out, n, window, 0);
+}
+int bls_g2_wnaf_mul_window_batch(bls_ctx* ctx, const bls_g2* b, const bls_fr_repr* k, bls_g2* out, size_t n, int window) {
+  if (window < 2 || window > BLS_MAX_WNAF_WINDOW) return BLS_ERR_INVALID_ARGUMENT;
+  return wnaf_host(ctx, 2, b, k, out, n, window, 0);
+}
+int bls_g1_mul_batch(bls_ctx* ctx, const bls_g1* b, const bls_fr_repr* k, bls_g1* out, size_t n) { return wnaf_host(ctx, 1, b, k, out, n, 0, 1); }
+int bls_g2_mul_batch(bls_ctx* ctx, const bls_g2* b, const bls_fr_repr* k, bls_g2* out, size_t n) { return wnaf_host(ctx, 2, b, k, out, n, 0, 1); }
+
+static int bn_host(bls_ctx* ctx, int degree, void* inout, size_t n) {
+  if (!ctx || (n && !inout)) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
+  H2D(dv, inout, n * pb);
+  DALLOC(dscr, bls_batch_normalization_scratch_bytes(ctx, degree, n));
+  if (degree == 2) TRY(bls_g2_batch_normalization_dev(ctx, (bls_g2*)dv.p, n, dscr.p, nullptr));
+  else TRY(bls_g1_batch_normalization_dev(ctx, (bls_g1*)dv.p, n, dscr.p, nullptr));
+  D2H(inout, dv, n * pb);
+  SYNC();
+  return BLS_OK;
+}
+int bls_g1_batch_normalization(bls_ctx* ctx, bls_g1* inout, size_t n) { return bn_host(ctx, 1, inout, n); }
+int bls_g2_batch_normalization(bls_ctx* ctx, bls_g2* inout, size_t n) { return bn_host(ctx, 2, inout, n); }
+
+static int into_affine_host(bls_ctx* ctx, int degree, const void* in, void* out, size_t n) {
+  if (!ctx || (n && (!in || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
+  size_t ab = degree == 2 ? sizeof(bls_g2_affine) : sizeof(bls_g1_affine);
+  H2D(din, in, n * pb);
+  DALLOC(dout, n * ab);
+  if (degree == 2) k_into_affine<Fp2><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)din.p, (uint64_t*)dout.p, n);
+  else k_into_affine<Fp><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)din.p, (uint64_t*)dout.p, n);
+  LAUNCH_CHECK();
+  D2H(out, dout, n * ab);
+  SYNC();
+  return BLS_OK;
+}
+int bls_g1_into_affine_batch(bls_ctx* ctx, const bls_g1* in, bls_g1_affine* out, size_t n) { return into_affine_host(ctx, 1, in, out, n); }
+int bls_g2_into_affine_batch(bls_ctx* ctx, const bls_g2* in, bls_g2_affine* out, size_t n) { return into_affine_host(ctx, 2, in, out, n); }
+
+static int pt_op_host(bls_ctx* ctx, int degree, int op, const void* a, const void* b, void* out, size_t n) {
+  bool needs_b = op == BLS_PT_ADD || op == BLS_PT_SUB || op == BLS_PT_ADD_MIXED;
+  bool known = needs_b || op == BLS_PT_DOUBLE || op == BLS_PT_NEGATE;
+  if (!ctx || !known || (n && (!a || !out || (needs_b && !b)))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
+  size_t ab = degree == 2 ? sizeof(bls_g2_affine) : sizeof(bls_g1_affine);
+  H2D(da, a, n * pb);
+  H2D(db, needs_b ? b : nullptr, needs_b ? n * (op == BLS_PT_ADD_MIXED ? ab : pb) : 1);
+  DALLOC(dout, n * pb);
+  if (degree == 2) k_pt_op<Fp2><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>(op, (const uint64_t*)da.p, (const uint64_t*)db.p, (uint64_t*)dout.p, n);
+  else k_pt_op<Fp><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>(op, (const uint64_t*)da.p, (const uint64_t*)db.p, (uint64_t*)dout.p, n);
+  LAUNCH_CHECK();
+  D2H(out, dout, n * pb);
+  SYNC();
+  return BLS_OK;
+}
+int bls_g1_op_batch(bls_ctx* ctx, int op, const bls_g1* a, const void* b, bls_g1* out, size_t n) { return pt_op_host(ctx, 1, op, a, b, out, n); }
+int bls_g2_op_batch(bls_ctx* ctx, int op, const bls_g2* a, const void* b, bls_g2* out, size_t n) { return pt_op_host(ctx, 2, op, a, b, out, n); }
+
+int bls_field_op_batch(bls_ctx* ctx, int degree, int op, const void* a, const void* b, void* out, uint8_t* ok, size_t n) {
+  if (!ctx || (n && (!a || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (degree != 1 && degree != 2 && degree != 6 && degree != 12) return BLS_ERR_INVALID_ARGUMENT;
+  // which ops exist at which degree (mirrors the switch statements of the kernels)
+  bool valid = false, binary = false;
+  switch (op) {
+    case BLS_OP_ADD: case BLS_OP_SUB: valid = degree != 12; binary = true; break;
+    case BLS_OP_MUL: valid = true; binary = true; break;
+    case BLS_OP_SQR: case BLS_OP_INV: valid = true; break;
+    case BLS_OP_NEG: valid = degree != 12; break;
+    case BLS_OP_DBL: valid = degree <= 2; break;
+    case BLS_OP_FROM_REPR: case BLS_OP_INTO_REPR: valid = degree == 1; break;
+    case BLS_OP_MUL_NONRES: valid = degree == 2 || degree == 6; break;
+    case BLS_OP_FROB1: valid = degree >= 2; break;
+    case BLS_OP_FROB2: case BLS_OP_FROB3: valid = degree >= 6; break;
+    case BLS_OP_CONJ: valid = degree == 12; break;
+    case BLS_OP_MUL_BY_014: valid = degree == 12; binary = true; break;
+    case BLS_OP_MUL_BY_01: case BLS_OP_MUL_BY_1: valid = degree == 6; binary = true; break;
+  }
+  if (!valid || (binary && n && !b)) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  size_t eb = (size_t)degree * sizeof(bls_fq);
+  H2D(da, a, n * eb);
+  H2D(db, binary ? b : nullptr, binary ? n * eb : 1);
+  DALLOC(dout, n * eb);
+  DALLOC(dok, n);
+  const uint64_t* pb = binary ? (const uint64_t*)db.p : nullptr;
+  unsigned g = blocks_for(n, TPB);
+  switch (degree) {
+    case 1: k_fq_op<<<g, TPB, 0, ctx->stream>>>(op, (const uint64_t*)da.p, pb, (uint64_t*)dout.p, (uint8_t*)dok.p, n); break;
+    case 2: k_fq2_op<<<g, TPB, 0, ctx->stream>>>(op, (const uint64_t*)da.p, pb, (uint64_t*)dout.p, (uint8_t*)dok.p, n); break;
+    case 6: k_fq6_op<<<g, TPB, 0, ctx->stream>>>(op, (const uint64_t*)da.p, pb, (uint64_t*)dout.p, (uint8_t*)dok.p, n); break;
+    case 12: k_fq12_op<<<g, TPB, 0, ctx->stream>>>(op, (const uint64_t*)da.p, pb, (uint64_t*)dout.p, (uint8_t*)dok.p, n); break;
+  }
+  LAUNCH_CHECK();
+  D2H(out, dout, n * eb);
+  if (ok) D2H(ok, dok, n);
+  SYNC();
+  return BLS_OK;
+}
+
+int bls_imad_peak(bls_ctx* ctx, int variant, int iters, double* macs_per_s, double* ms_out) {
+  if (!ctx || !macs_per_s || iters <= 0 || variant < 0 || variant > 3) return BLS_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  DALLOC(sink, 8);
+  const int threads = 256;
+  const unsigned blocks = (unsigned)ctx->sm_count * 8;   // 2048 threads per SM: full occupancy
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; rep++) {   // rep 0 is the warm-up
+    CK(cudaEventRecord(e0, ctx->stream));
+    if (variant == 0) k_imad_wide_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, iters, (uint64_t*)sink.p);
+    else if (variant == 1) k_fpmul_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, iters, (uint64_t*)sink.p);
+    else if (variant == 3) k_carry_row_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, iters, (uint64_t*)sink.p);
+    else k_imad32_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, iters, (uint64_t*)sink.p);
+    LAUNCH_CHECK();
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double per_thread = variant == 1 ? 2.0 * 300.0 * iters : variant == 3 ? 8.0 * 24.0 * iters : (double)PEAK_CHAINS * PEAK_UNROLL * iters;
+  double total = per_thread * threads * blocks;
+  *macs_per_s = total / (best * 1e-3);
+  if (ms_out) *ms_out = best;
+  return BLS_OK;
+}
+
+}  // extern "C"
