@@ -62,16 +62,18 @@ template <class F> __device__ __noinline__ void pt_double(Jac<F>& s) {
   s.y = f_sub(f_mul(f_sub(d, s.x), e), c);
 }
 
-template <class F> __device__ __noinline__ void pt_add(Jac<F>& s, const Jac<F>& o) {
-  if (pt_is_zero(s)) { s = o; return; }
-  if (pt_is_zero(o)) return;
+// Returns true when the operands are equal and the caller has to double instead (ec.rs:394-396);
+// the doubling is issued by the inline wrapper below, not from inside this function.
+template <class F> __device__ __noinline__ bool pt_add_core(Jac<F>& s, const Jac<F>& o) {
+  if (pt_is_zero(s)) { s = o; return false; }
+  if (pt_is_zero(o)) return false;
   F z1z1 = f_sqr(s.z);
   F z2z2 = f_sqr(o.z);
   F u1 = f_mul(s.x, z2z2);
   F u2 = f_mul(o.x, z1z1);
   F s1 = f_mul(f_mul(s.y, o.z), z2z2);
   F s2 = f_mul(f_mul(o.y, s.z), z1z1);
-  if (f_eq(u1, u2) && f_eq(s1, s2)) { pt_double(s); return; }
+  if (f_eq(u1, u2) && f_eq(s1, s2)) return true;
   F h = f_sub(u2, u1);
   F i = f_sqr(f_dbl(h));
   F j = f_mul(h, i);
@@ -80,15 +82,19 @@ template <class F> __device__ __noinline__ void pt_add(Jac<F>& s, const Jac<F>& 
   s.x = f_sub(f_sub(f_sub(f_sqr(r), j), v), v);
   s.y = f_sub(f_mul(f_sub(v, s.x), r), f_dbl(f_mul(s1, j)));
   s.z = f_mul(f_sub(f_sub(f_sqr(f_add(s.z, o.z)), z1z1), z2z2), h);
+  return false;
+}
+template <class F> __device__ __forceinline__ void pt_add(Jac<F>& s, const Jac<F>& o) {
+  if (pt_add_core(s, o)) pt_double(s);
 }
 
-template <class F> __device__ __noinline__ void pt_add_mixed(Jac<F>& s, const Aff<F>& o) {
-  if (o.inf) return;
-  if (pt_is_zero(s)) { s.x = o.x; s.y = o.y; f_set_one(s.z); return; }
+template <class F> __device__ __noinline__ bool pt_add_mixed_core(Jac<F>& s, const Aff<F>& o) {
+  if (o.inf) return false;
+  if (pt_is_zero(s)) { s.x = o.x; s.y = o.y; f_set_one(s.z); return false; }
   F z1z1 = f_sqr(s.z);
   F u2 = f_mul(o.x, z1z1);
   F s2 = f_mul(f_mul(o.y, s.z), z1z1);
-  if (f_eq(s.x, u2) && f_eq(s.y, s2)) { pt_double(s); return; }
+  if (f_eq(s.x, u2) && f_eq(s.y, s2)) return true;
   F h = f_sub(u2, s.x);
   F hh = f_sqr(h);
   F i = f_dbl(f_dbl(hh));
@@ -99,6 +105,10 @@ template <class F> __device__ __noinline__ void pt_add_mixed(Jac<F>& s, const Af
   F y3 = f_sub(f_mul(f_sub(v, x3), r), f_dbl(f_mul(j, s.y)));
   s.z = f_sub(f_sub(f_sqr(f_add(s.z, h)), z1z1), hh);
   s.x = x3; s.y = y3;
+  return false;
+}
+template <class F> __device__ __forceinline__ void pt_add_mixed(Jac<F>& s, const Aff<F>& o) {
+  if (pt_add_mixed_core(s, o)) pt_double(s);
 }
 
 // ec.rs:528-532

@@ -43,8 +43,9 @@ def fn_body(src, name):
 def const_body(src, name):
     i = src.index("const %s:" % name)
     line = src.count("\n", 0, i) + 1
-    j = src.index(";", i)
-    return src[i:j], line
+    e = src.index(" = ", i)
+    j = src.index(";\n", e)          # the terminating ';' of the item (skips the one inside `[Fq; 2]`)
+    return src[e:j], line
 
 
 kats = {}

@@ -1,0 +1,271 @@
+"""Pins the oracle (oracle/bls_model.py and oracle/bls_oracle.c) on the reference's OWN known-answer
+vectors (tests/golden/reference_kats.json, extracted by tests/golden/make_golden.py from the #[test]
+functions of /root/reference/src/bls12_381/{fq,fq2,ec}.rs and tests/mod.rs) and on the k*G vector files.
+CPU only."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import bls_model as m
+import oracle_lib as o
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+KATS = json.load(open(os.path.join(GOLD, "reference_kats.json")))
+
+
+def R(name):
+    return [int(x, 16) for x in KATS[name]["reprs"]]
+
+
+def limbs(x, n=6):
+    return np.array([m.limbs64(x, n)], dtype=np.uint64)
+
+
+def fq_from_repr(x):
+    """Fq::from_repr(FqRepr(x)) through the C oracle -> Montgomery limbs (1,6)."""
+    out, ok = o.fq_op("from_repr", limbs(x))
+    assert ok[0] == 1
+    return out
+
+
+def test_montgomery_constants():
+    """fq.rs:6-43, 501-508, 69-76: MODULUS, R, R2, INV, NEGATIVE_ONE, B_COEFF as quoted by the reference."""
+    assert R("const_MODULUS") == [m.Q]
+    assert R("const_R") == [m.MONT_R]
+    assert R("const_R2") == [m.MONT_R2]
+    assert R("const_INV") == [m.INV64]
+    assert R("const_NEGATIVE_ONE") == [m.to_mont(m.Q - 1)]
+    assert R("const_B_COEFF") == [m.to_mont(4)]
+    # the same through the C oracle: from_repr(4) == B_COEFF (fq.rs:1174-1176), -one (fq.rs:1890-1895)
+    assert fq_from_repr(4).tobytes() == limbs(R("const_B_COEFF")[0]).tobytes()
+    one = limbs(m.MONT_R)
+    assert o.fq_op("neg", one)[0].tobytes() == limbs(R("const_NEGATIVE_ONE")[0]).tobytes()
+
+
+def test_generators():
+    """fq.rs:85-136"""
+    g1, g2 = o.generators()
+    want1 = [R("const_G1_GENERATOR_X")[0], R("const_G1_GENERATOR_Y")[0]]
+    assert [m.from_limbs64(g1[0, :6]), m.from_limbs64(g1[0, 6:12])] == want1
+    want2 = [R("const_G2_GENERATOR_" + s)[0] for s in ("X_C0", "X_C1", "Y_C0", "Y_C1")]
+    assert [m.from_limbs64(g2[0, 6 * i:6 * i + 6]) for i in range(4)] == want2
+    assert want1 == [m.to_mont(m.G1_X), m.to_mont(m.G1_Y)]
+    assert want2 == [m.to_mont(v) for v in (m.G2_X[0], m.G2_X[1], m.G2_Y[0], m.G2_Y[1])]
+
+
+def test_frobenius_tables_match_reference_entries():
+    """fq.rs:1179-1887 re-derives every table entry with pow(); here the derived tables are compared
+    with the c0/c1 limbs the reference source quotes (fq.rs:139-498)."""
+    assert R("const_FROBENIUS_COEFF_FQ2_C1") == [m.to_mont(v) for v in m.FROB_FQ2_C1]
+    for name, table in (("FQ6_C1", m.FROB_FQ6_C1), ("FQ6_C2", m.FROB_FQ6_C2), ("FQ12_C1", m.FROB_FQ12_C1)):
+        want = R("const_FROBENIUS_COEFF_" + name)
+        assert len(want) == 2 * len(table)
+        assert want == [m.to_mont(c) for e in table for c in e]
+    # algebraic definition check (what the reference test does): coefficient = nonresidue^((q^i-1)/k)
+    for i in range(1, 6):
+        assert m.fq2_pow(m.FROB_FQ6_C1[i], 3) == m.fq2_pow(m.NONRES, m.Q ** i - 1)
+        assert m.FROB_FQ6_C2[i] == m.fq2_mul(m.FROB_FQ6_C1[i], m.FROB_FQ6_C1[i])
+    for i in range(1, 12):
+        assert m.fq2_mul(m.FROB_FQ12_C1[i], m.FROB_FQ12_C1[i]) == m.FROB_FQ6_C1[i % 6]
+
+
+def test_fq_mul_kat():
+    """fq.rs:2558-2584 (Montgomery-form operands and result)"""
+    a, b, c = R("test_fq_mul_assign")
+    assert o.fq_op("mul", limbs(a), limbs(b))[0].tobytes() == limbs(c).tobytes()
+    assert m.to_mont(m.fq_mul(m.from_mont(a), m.from_mont(b))) == c
+
+
+def test_fq_square_kat():
+    """fq.rs:2630-2651"""
+    a, c = R("test_fq_squaring")
+    assert o.fq_op("sqr", limbs(a))[0].tobytes() == fq_from_repr(c).tobytes()
+
+
+def test_fq_from_into_repr_kat():
+    """fq.rs:2778-2822: q is not in the field; from_repr(a) * from_repr(b) == from_repr(c)"""
+    reprs = R("test_fq_from_into_repr")
+    a, b, c = reprs[-3:]
+    assert o.fq_op("from_repr", limbs(m.Q))[1][0] == 0
+    prod = o.fq_op("mul", fq_from_repr(a), fq_from_repr(b))[0]
+    assert o.fq_op("into_repr", prod)[0].tobytes() == limbs(c).tobytes()
+    assert (a * b) % m.Q == c
+
+
+def test_fq_add_sub_kats():
+    """fq.rs:2325-2425, 2452-2537: the quoted operands/results obey the group law in the model and in C,
+    including the wrap-around cases q-1 + 1 = 0 and 0 - 1 = q-1."""
+    one, qm1 = limbs(1), limbs(m.Q - 1)
+    assert o.fq_op("add", qm1, one)[0].tobytes() == limbs(0).tobytes()
+    assert o.fq_op("sub", limbs(0), one)[0].tobytes() == qm1.tobytes()
+    vals = [v for v in R("test_fq_add_assign") + R("test_fq_sub_assign") if v < m.Q]
+    a = np.array([m.limbs64(v) for v in vals], dtype=np.uint64)
+    b = np.roll(a, 1, axis=0)
+    s = o.fq_op("add", a, b)[0]
+    d = o.fq_op("sub", a, b)[0]
+    for i, (x, y) in enumerate(zip(vals, vals[-1:] + vals[:-1])):
+        assert m.from_limbs64(s[i]) == (x + y) % m.Q
+        assert m.from_limbs64(d[i]) == (x - y) % m.Q
+    # first add KAT: tmp + 1 (fq.rs:2352-2364)
+    r = R("test_fq_add_assign")
+    assert o.fq_op("add", limbs(r[0]), one)[0].tobytes() == limbs(r[2]).tobytes()
+
+
+def _fq2(c0, c1):
+    return np.concatenate([fq_from_repr(c0), fq_from_repr(c1)], axis=1)
+
+
+def test_fq2_kats():
+    """fq2.rs:273-457: squaring, multiplication and inverse known answers"""
+    r = R("test_fq2_mul")
+    assert o.fq2_op("mul", _fq2(r[0], r[1]), _fq2(r[2], r[3]))[0].tobytes() == _fq2(r[4], r[5]).tobytes()
+    r = R("test_fq2_squaring")
+    assert o.fq2_op("sqr", _fq2(r[0], r[1]))[0].tobytes() == _fq2(r[2], r[3]).tobytes()
+    r = R("test_fq2_inverse")
+    out, ok = o.fq2_op("inv", _fq2(r[0], r[1]))
+    assert ok[0] == 1 and out.tobytes() == _fq2(r[2], r[3]).tobytes()
+    assert o.fq2_op("inv", np.zeros((1, 12), dtype=np.uint64))[1][0] == 0
+    r = R("test_fq2_addition")
+    assert o.fq2_op("add", _fq2(r[0], r[1]), _fq2(r[2], r[3]))[0].tobytes() == _fq2(r[4], r[5]).tobytes()
+    r = R("test_fq2_subtraction")
+    assert o.fq2_op("sub", _fq2(r[0], r[1]), _fq2(r[2], r[3]))[0].tobytes() == _fq2(r[4], r[5]).tobytes()
+    r = R("test_fq2_negation")
+    assert o.fq2_op("neg", _fq2(r[0], r[1]))[0].tobytes() == _fq2(r[2], r[3]).tobytes()
+    r = R("test_fq2_doubling")
+    assert o.fq2_op("dbl", _fq2(r[0], r[1]))[0].tobytes() == _fq2(r[2], r[3]).tobytes()
+    r = R("test_fq2_frobenius_map")   # fq2.rs:682-792: frobenius^0 = id, ^1 = conj, ^1 again = id, ^2 = id
+    a = _fq2(r[0], r[1])
+    f1 = o.fq2_op("frob1", a)[0]
+    assert f1.tobytes() == _fq2(r[4], r[5]).tobytes()
+    assert o.fq2_op("frob1", f1)[0].tobytes() == a.tobytes()
+
+
+def _g1a(x, y):
+    return np.concatenate([fq_from_repr(x), fq_from_repr(y), np.zeros((1, 1), dtype=np.uint64)], axis=1)
+
+
+def _g2a(r):
+    return np.concatenate([_fq2(r[0], r[1]), _fq2(r[2], r[3]), np.zeros((1, 1), dtype=np.uint64)], axis=1)
+
+
+def test_g1_add_double_kats():
+    """ec.rs:1060-1175: G1 addition / doubling results in affine form"""
+    r = R("test_g1_addition_correctness")
+    p, q, want = _g1a(r[0], r[1]), _g1a(r[2], r[3]), _g1a(r[4], r[5])
+    s = o.g1_op("add", o.g1_from_affine(p), o.g1_from_affine(q))
+    assert o.g1_into_affine(s).tobytes() == want.tobytes()
+    r = R("test_g1_doubling_correctness")
+    d = o.g1_op("double", o.g1_from_affine(_g1a(r[0], r[1])))
+    assert o.g1_into_affine(d).tobytes() == _g1a(r[2], r[3]).tobytes()
+
+
+def test_g1_same_y_kat():
+    """ec.rs:1178-1262: different x, same y -- add_assign and add_assign_mixed agree with the quoted c"""
+    r = R("test_g1_same_y")
+    a, b, c = _g1a(r[0], r[1]), _g1a(r[2], r[3]), _g1a(r[4], r[5])
+    t1 = o.g1_op("add", o.g1_from_affine(a), o.g1_from_affine(b))
+    assert o.g1_into_affine(t1).tobytes() == c.tobytes()
+    t2 = o.g1_op("add_mixed", o.g1_from_affine(a), b)
+    assert o.g1_into_affine(t2).tobytes() == c.tobytes()
+
+
+def test_g2_add_double_kats():
+    """ec.rs:1802-2017"""
+    r = R("test_g2_addition_correctness")
+    p, q, want = _g2a(r[0:4]), _g2a(r[4:8]), _g2a(r[8:12])
+    s = o.g2_op("add", o.g2_from_affine(p), o.g2_from_affine(q))
+    assert o.g2_into_affine(s).tobytes() == want.tobytes()
+    r = R("test_g2_doubling_correctness")
+    d = o.g2_op("double", o.g2_from_affine(_g2a(r[0:4])))
+    assert o.g2_into_affine(d).tobytes() == _g2a(r[4:8]).tobytes()
+
+
+def test_relic_pairing_kat():
+    """tests/mod.rs:5-53: e(G1::one(), G2::one()) == the RELIC value, in the model, in C, and in the
+    committed fixture the GPU test compares against."""
+    want = [int(x) for x in KATS["test_pairing_result_against_relic"]["decimal"]]
+    assert len(want) == 12
+    assert m.flatten(m.pairing(m.G1_GEN_AFFINE, m.G2_GEN_AFFINE)) == want
+    g1, g2 = o.generators()
+    e = o.pairing(g1, g2)
+    assert [m.from_mont(m.from_limbs64(e[0, 6 * i:6 * i + 6])) for i in range(12)] == want
+    assert e.tobytes() == open(os.path.join(GOLD, "relic_pairing_g1g2.bin"), "rb").read()
+
+
+# ---- k*G serialisation vectors (tests/mod.rs:55-97; format: bls12_381/README.md:59-70, ec.rs:690-822)
+def _encode_fq(x):
+    return x.to_bytes(48, "big")
+
+
+def _enc_uncompressed(pt, g2):
+    x, y, inf = pt
+    size = 192 if g2 else 96
+    if inf:
+        b = bytearray(size); b[0] |= 1 << 6
+        return bytes(b)
+    if g2:
+        return _encode_fq(x[1]) + _encode_fq(x[0]) + _encode_fq(y[1]) + _encode_fq(y[0])   # c1 then c0 (ec.rs:1371-1374)
+    return _encode_fq(x) + _encode_fq(y)
+
+
+def _enc_compressed(pt, g2):
+    x, y, inf = pt
+    size = 96 if g2 else 48
+    if inf:
+        b = bytearray(size); b[0] |= (1 << 7) | (1 << 6)
+        return bytes(b)
+    if g2:
+        b = bytearray(_encode_fq(x[1]) + _encode_fq(x[0]))
+        negy = m.fq2_neg(y)
+        greatest = (y[1], y[0]) > (negy[1], negy[0])          # Fq2 ordering: c1 first (fq2.rs:21-31)
+    else:
+        b = bytearray(_encode_fq(x))
+        greatest = y > (m.Q - y) % m.Q
+    b[0] |= 1 << 7
+    if greatest:
+        b[0] |= 1 << 5
+    return bytes(b)
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_generator_multiples_vectors(g2):
+    """e = 0; 1000 times { encode(e.into_affine()); e += one } must reproduce the .dat files byte for byte,
+    both through the C oracle (add_assign + into_affine on Montgomery limbs) and the big-int model."""
+    F = m._F2 if g2 else m._F1
+    gen = m.G2_GEN_AFFINE if g2 else m.G1_GEN_AFFINE
+    name = "g2" if g2 else "g1"
+    want_u = open(os.path.join(GOLD, name + "_uncompressed_multiples.bin"), "rb").read()
+    want_c = open(os.path.join(GOLD, name + "_compressed_multiples.bin"), "rb").read()
+    # C oracle: running sum with projective add_assign, then per-point into_affine
+    g1a, g2a = o.generators()
+    one = (o.g2_from_affine if g2 else o.g1_from_affine)(g2a if g2 else g1a)
+    w = 36 if g2 else 18
+    acc = np.zeros((1, w), dtype=np.uint64)
+    acc[0, w // 3:w // 3 + 6] = np.array(m.limbs64(m.MONT_R), dtype=np.uint64)   # zero() = (0, 1, 0)
+    pts = np.zeros((1000, w), dtype=np.uint64)
+    op = o.g2_op if g2 else o.g1_op
+    for k in range(1000):
+        pts[k] = acc[0]
+        acc = op("add", acc, one)
+    aff = (o.g2_into_affine if g2 else o.g1_into_affine)(pts)
+    got_u, got_c = bytearray(), bytearray()
+    e_model = m.pt_zero(F)
+    gen_j = m.pt_from_affine(F, gen)
+    for k in range(1000):
+        row = aff[k]
+        if g2:
+            x = (m.from_mont(m.from_limbs64(row[0:6])), m.from_mont(m.from_limbs64(row[6:12])))
+            y = (m.from_mont(m.from_limbs64(row[12:18])), m.from_mont(m.from_limbs64(row[18:24])))
+            pt = (x, y, bool(row[24]))
+        else:
+            pt = (m.from_mont(m.from_limbs64(row[0:6])), m.from_mont(m.from_limbs64(row[6:12])), bool(row[12]))
+        if k < 40:   # the big-int model agrees with the C oracle point by point (and on the Jacobian triple)
+            assert m.pt_to_affine(F, e_model) == pt
+            assert m.to_bytes(e_model) == pts[k].tobytes()
+            e_model = m.pt_add(F, e_model, gen_j)
+        got_u += _enc_uncompressed(pt, g2)
+        got_c += _enc_compressed(pt, g2)
+    assert bytes(got_u) == want_u
+    assert bytes(got_c) == want_c

@@ -3,18 +3,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, ROOT + "/oracle", ROOT + "/tests"]
 import numpy as np
 import pairing_b200._native as nat, oracle_lib as o, datagen as dg
-a = dg.g1_points(32, 22); b = dg.g1_points(32, 23)
-cases = {"plain": (a, b)}
-a2 = a.copy(); a2[0] = 0; a2[0, 6:12] = np.array(__import__("bls_model").limbs64(__import__("bls_model").MONT_R), dtype=np.uint64)
-cases["a_inf"] = (a2, b)
-cases["b_inf"] = (b, a2)
-cases["equal"] = (a, a.copy())
-cases["neg"] = (a, o.g1_op("negate", a))
-for name, (x, y) in cases.items():
+n = 128
+a = dg.g1_points(n, 22, infinity_at=(0, 5)); b = dg.g1_points(n, 23, infinity_at=(1, 5))
+def run(name, op, x, y):
     try:
         ctx = nat.Context(0)
-        got = ctx.g1_op("add", x, y)
-        print(name, "ok" if np.array_equal(got, o.g1_op("add", x, y)) else "MISMATCH", flush=True)
+        got = ctx.g1_op(op, x, y)
+        print(name, op, "ok" if np.array_equal(got, o.g1_op(op, x, y)) else "MISMATCH", flush=True)
+        return True
     except Exception as e:
-        print(name, "EXC", str(e)[:150], flush=True)
-        break
+        print(name, op, "EXC", str(e)[:120], flush=True)
+        return False
+ok = run("inf-mix", "add", a, b)
+b1 = b.copy(); b1[10] = a[10]
+ok = ok and run("+equal", "add", a, b1)
+b2 = b1.copy(); b2[11] = o.g1_op("negate", a[11:12])[0]
+ok = ok and run("+neg", "add", a, b2)
+b3 = b2.copy(); b3[12] = o.g1_op("double", a[12:13])[0]
+ok = ok and run("+dbl", "add", a, b3)
+ok = ok and run("all", "sub", a, b3)
+ok = ok and run("plain", "sub", dg.g1_points(n, 1), dg.g1_points(n, 2))

@@ -158,6 +158,113 @@ __global__ void __launch_bounds__(256) k_clock_probe(uint32_t seed, int iters, u
   if (x.v[0] == 0x1234567u && y.v[3] == 7u && sacc == 99) out[2] = x.v[1];
 }
 
+// ablations of the product: FLAGS bit0 = no final conditional subtract, bit1 = no merge at all,
+// bit2 = m does not depend on the accumulator, bit3 = no m*q rows at all (a*b rows only)
+template <int FLAGS>
+__device__ __forceinline__ Fp mul_abl(const Fp& a, const Fp& b, uint32_t mconst) {
+  uint32_t e[12], o[12];
+#pragma unroll
+  for (int j = 0; j < 12; j++) { e[j] = a.v[j]; o[j] = b.v[j]; }
+#pragma unroll
+  for (int i = 0; i < 12; i += 2) {
+    fp_madc_rshift_row(e[0], o[1], o, &a.v[1], b.v[i]);
+    fp_cmad_row(e, &a.v[0], b.v[i], o[11]);
+    if (!(FLAGS & 8)) {
+      uint32_t m = (FLAGS & 4) ? mconst : e[0] * BLS_NINV;
+      fp_cmad_q_odd(o, m); fp_cmad_q_even(e, m, o[11]);
+    }
+    fp_madc_rshift_row(o[0], e[1], e, &a.v[1], b.v[i + 1]);
+    fp_cmad_row(o, &a.v[0], b.v[i + 1], e[11]);
+    if (!(FLAGS & 8)) {
+      uint32_t m = (FLAGS & 4) ? mconst + i : o[0] * BLS_NINV;
+      fp_cmad_q_odd(e, m); fp_cmad_q_even(o, m, e[11]);
+    }
+  }
+  Fp r;
+  if (FLAGS & 2) {
+#pragma unroll
+    for (int j = 0; j < 12; j++) r.v[j] = e[j] ^ o[j];
+    return r;
+  }
+  if (FLAGS & 1) {
+    asm("add.cc.u32 %0, %12, %23;\n\taddc.cc.u32 %1, %13, %24;\n\taddc.cc.u32 %2, %14, %25;\n\taddc.cc.u32 %3, %15, %26;\n\t"
+        "addc.cc.u32 %4, %16, %27;\n\taddc.cc.u32 %5, %17, %28;\n\taddc.cc.u32 %6, %18, %29;\n\taddc.cc.u32 %7, %19, %30;\n\t"
+        "addc.cc.u32 %8, %20, %31;\n\taddc.cc.u32 %9, %21, %32;\n\taddc.cc.u32 %10, %22, %33;\n\taddc.u32 %11, %34, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+          "=r"(r.v[7]), "=r"(r.v[8]), "=r"(r.v[9]), "=r"(r.v[10]), "=r"(r.v[11])
+        : "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]),
+          "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]), "r"(e[8]), "r"(e[9]), "r"(e[10]), "r"(e[11]));
+    return r;
+  }
+  return fp_merge(o, e);
+}
+template <int FLAGS>
+__global__ void __launch_bounds__(256, 2) k_abl(uint32_t seed, int iters, uint32_t* sink, uint32_t zero) {
+  Fp x = fp_one(), y = fp_r2();
+  x.v[0] ^= seed ^ threadIdx.x; y.v[1] ^= seed;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) { x = mul_abl<FLAGS>(x, y, seed + it); y = mul_abl<FLAGS>(y, x, seed ^ it); }
+  if (x.v[0] == 0x1234567u && y.v[3] == 7u) sink[0] = x.v[1];
+}
+
+// row-form probes.  FORM 0: cmad rows, same b.  1: cmad rows, b varies per row.  2: rshift rows only.
+// 3: rshift + cmad alternating (the a*b rows of the product).  4: like 3 but the rshift row starts a fresh carry chain.
+__device__ __forceinline__ void rshift_row_nocarry(uint32_t (&acc)[12], const uint32_t* x, uint32_t b) {
+  asm("mad.lo.cc.u32 %0, %12, %18, %2;\n\tmadc.hi.cc.u32 %1, %12, %18, %3;\n\t"
+      "madc.lo.cc.u32 %2, %13, %18, %4;\n\tmadc.hi.cc.u32 %3, %13, %18, %5;\n\t"
+      "madc.lo.cc.u32 %4, %14, %18, %6;\n\tmadc.hi.cc.u32 %5, %14, %18, %7;\n\t"
+      "madc.lo.cc.u32 %6, %15, %18, %8;\n\tmadc.hi.cc.u32 %7, %15, %18, %9;\n\t"
+      "madc.lo.cc.u32 %8, %16, %18, %10;\n\tmadc.hi.cc.u32 %9, %16, %18, %11;\n\t"
+      "madc.lo.cc.u32 %10, %17, %18, 0;\n\tmadc.hi.u32 %11, %17, %18, 0;"
+      : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]),
+        "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8]), "+r"(acc[9]), "+r"(acc[10]), "+r"(acc[11])
+      : "r"(x[0]), "r"(x[2]), "r"(x[4]), "r"(x[6]), "r"(x[8]), "r"(x[10]), "r"(b));
+}
+template <int FORM>
+__global__ void __launch_bounds__(256, 2) k_rowform(uint32_t seed, int iters, uint32_t* sink, uint32_t zero) {
+  uint32_t e[12], o[12], x[12], b[12];
+#pragma unroll
+  for (int k = 0; k < 12; k++) { e[k] = seed + k; o[k] = seed * 3 + k; x[k] = (seed ^ threadIdx.x) * (2 * k + 1) + 1; b[k] = x[k] * 77 + k; }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) {
+      if (FORM == 0) { fp_cmad_row(e, &x[0], b[0], o[11]); fp_cmad_row(o, &x[1], b[0], e[11]); fp_cmad_row(e, &x[0], b[0], o[11]); fp_cmad_row(o, &x[1], b[0], e[11]); }
+      if (FORM == 1) { fp_cmad_row(e, &x[0], b[i], o[11]); fp_cmad_row(o, &x[1], b[i], e[11]); fp_cmad_row(e, &x[0], b[i + 1], o[11]); fp_cmad_row(o, &x[1], b[i + 1], e[11]); }
+      if (FORM == 2) { fp_madc_rshift_row(e[0], o[1], o, &x[1], b[i]); fp_madc_rshift_row(o[0], e[1], e, &x[1], b[i]);
+                       fp_madc_rshift_row(e[0], o[1], o, &x[1], b[i + 1]); fp_madc_rshift_row(o[0], e[1], e, &x[1], b[i + 1]); }
+      if (FORM == 3) { fp_madc_rshift_row(e[0], o[1], o, &x[1], b[i]); fp_cmad_row(e, &x[0], b[i], o[11]);
+                       fp_madc_rshift_row(o[0], e[1], e, &x[1], b[i + 1]); fp_cmad_row(o, &x[0], b[i + 1], e[11]); }
+      if (FORM == 4) { rshift_row_nocarry(o, &x[1], b[i]); fp_cmad_row(e, &x[0], b[i], o[11]);
+                       rshift_row_nocarry(e, &x[1], b[i + 1]); fp_cmad_row(o, &x[0], b[i + 1], e[11]); }
+    }
+  }
+  uint32_t s2 = 0;
+#pragma unroll
+  for (int k = 0; k < 12; k++) s2 ^= e[k] ^ o[k];
+  if (s2 == 0x1234567u) sink[0] = s2;
+}
+
+// occupancy / ILP sweep: NCHAIN independent fp_mul chains per thread, MINB blocks per SM requested
+template <int NCHAIN, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_ilp(uint32_t seed, int iters, uint32_t* sink, uint32_t zero) {
+  uint32_t q[12] = {0};
+  Fp x[NCHAIN], y[NCHAIN];
+#pragma unroll
+  for (int c = 0; c < NCHAIN; c++) { x[c] = fp_one(); y[c] = fp_r2(); x[c].v[0] ^= seed ^ threadIdx.x ^ c; y[c].v[1] ^= seed + c; }
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int c = 0; c < NCHAIN; c++) x[c] = mul_t<0>(x[c], y[c], q);
+#pragma unroll
+    for (int c = 0; c < NCHAIN; c++) y[c] = mul_t<0>(y[c], x[c], q);
+  }
+  uint32_t s2 = 0;
+#pragma unroll
+  for (int c = 0; c < NCHAIN; c++) s2 ^= x[c].v[0] ^ y[c].v[3];
+  if (s2 == 0x1234567u) sink[0] = s2;
+}
+
 template <class K> static void run(const char* name, K kern, double macs_per_thread_iter, int iters) {
   uint32_t* sink; cudaMalloc(&sink, 64);
   int sm = 0; cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
@@ -181,6 +288,25 @@ int main() {
   run("fp_mul, q immediate", k_mul<0>, 600.0, 2000);
   run("fp_mul, q uniform registers", k_mul<1>, 600.0, 2000);
   run("fp_mul, q vector registers", k_mul<2>, 600.0, 2000);
+  run("rowform 0: cmad rows, same b", k_rowform<0>, 288.0, 2000);
+  run("rowform 1: cmad rows, b varies", k_rowform<1>, 288.0, 2000);
+  run("rowform 2: rshift rows only", k_rowform<2>, 288.0, 2000);
+  run("rowform 3: rshift + cmad (a*b rows)", k_rowform<3>, 288.0, 2000);
+  run("rowform 4: rshift(no carry-in) + cmad", k_rowform<4>, 288.0, 2000);
+  run("ablation: full (uniform rows)", k_abl<0>, 600.0, 2000);
+  run("ablation: no final sub", k_abl<1>, 600.0, 2000);
+  run("ablation: no merge", k_abl<2>, 600.0, 2000);
+  run("ablation: m independent, no merge", k_abl<6>, 600.0, 2000);
+  run("ablation: a*b rows only (300->144 MAC)", k_abl<10>, 288.0, 2000);
+  run("fp_mul x1 chain, minBlocks=1", k_ilp<1, 1>, 600.0, 2000);
+  run("fp_mul x1 chain, minBlocks=2", k_ilp<1, 2>, 600.0, 2000);
+  run("fp_mul x1 chain, minBlocks=3", k_ilp<1, 3>, 600.0, 2000);
+  run("fp_mul x1 chain, minBlocks=4", k_ilp<1, 4>, 600.0, 2000);
+  run("fp_mul x2 chains, minBlocks=1", k_ilp<2, 1>, 1200.0, 1000);
+  run("fp_mul x2 chains, minBlocks=2", k_ilp<2, 2>, 1200.0, 1000);
+  run("fp_mul x3 chains, minBlocks=1", k_ilp<3, 1>, 1800.0, 700);
+  run("fp_mul x3 chains, minBlocks=2", k_ilp<3, 2>, 1800.0, 700);
+  run("fp_mul x4 chains, minBlocks=1", k_ilp<4, 1>, 2400.0, 500);
   run("fp_mul rolled (6 x 2 rows)", k_mul_rolled, 600.0, 2000);
   run("fp_mul unrolled, one per iteration", k_mul_one, 600.0, 2000);
   {
