@@ -1,0 +1,378 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200 BLS12-381 pairing path.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload (BASELINE.json configs[1]): a batch of 2^16 independent full pairings (Miller loop + final
+exponentiation) per GPU per step, on synthetic subgroup points generated on the device by the
+engine's own wNAF kernels.  One "step" = one pass of the hot path over one batch.  N > 1: one rank
+per GPU (torchrun), every rank runs its own 2^16 batch (weak scaling, no data-path collective);
+`value` = pairings of all ranks / max-over-ranks device time.
+
+The JSON line carries, besides the base contract: `roofline` (integer-multiply bound: algorithmic
+MAC32/s against the IMAD.WIDE peak measured in the same run), `cpu_baseline` (the C oracle timed on
+the host cores, rank 0, bounded sample), `e2e` (same metric through the host-buffer C-ABI call,
+copies inside the timed region), `secondary` (G1 wNAF muls/s and sharded multi-Miller pairs/s).
+
+`--impl reference` times the reference's CPU algorithm (the C restatement in oracle/ -- the Rust
+crate cannot be built in this image) on all host threads, on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT]
+
+BATCH_LOG2 = 16
+MAC32_PER_PAIRING = 20621 * 300          # 20 621 Fq mul/sq x 300 MAC32
+MAC32_PER_G1_WNAF = 2577 * 300           # wNAF w=4 mul + batch normalisation
+MAC32_PER_MM_PAIR = 4684 * 300           # multi-Miller per pair incl. on-the-fly prepare
+HBM_BYTES_PER_PAIRING = 104 + 200 + 576  # G1Affine + G2Affine in, Fq12 out
+SEED = 0x5DBE62598D313D76
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-log2", type=int, default=BATCH_LOG2)
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the CPU algorithm on the host cores (rank 0 only)
+# ------------------------------------------------------------------------------------------------
+def oracle_inputs(n):
+    """n affine pairs for the CPU arms: small multiples of the generators built with the oracle."""
+    sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    import datagen as dg
+    return dg.g1_affine_points(n, 101), dg.g2_affine_points(n, 202)
+
+
+def cpu_pairings_per_s(sample, threads):
+    sys.path[:0] = [os.path.join(ROOT, "oracle")]
+    import oracle_lib as o
+    p, q = oracle_inputs(sample)
+    o.pairing(p[:threads], q[:threads], threads)          # warm-up (page in, spawn)
+    t0 = time.perf_counter()
+    o.pairing(p, q, threads)
+    dt = time.perf_counter() - t0
+    return sample / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path[:0] = [os.path.join(ROOT, "oracle")]
+    import oracle_lib as o
+    threads = o.default_threads()
+    p, q = oracle_inputs(max(threads * 8, 64))
+    # size one step to ~2 s of wall clock
+    t0 = time.perf_counter(); o.pairing(p, q, threads); probe = time.perf_counter() - t0
+    per_s = len(p) / probe
+    sample = max(threads, int(per_s * 2.0))
+    p, q = oracle_inputs(sample)
+    for _ in range(args.warmup):
+        o.pairing(p[:max(threads, sample // 8)], q[:max(threads, sample // 8)], threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.pairing(p, q, threads)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "BLS12-381 pairings/sec", "value": value, "unit": "pairings/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (6 x 64-bit Montgomery)",
+        "data": "synthetic",
+        "config": {"workload": "batch of independent full pairings (BASELINE configs[1]), bounded sample of %d pairings per step" % sample,
+                   "batch": sample},
+        "cpu_baseline": {"value": value, "unit": "pairings/s", "cores": threads, "kind": "port",
+                         "sample": "%d pairings per step x %d steps, C restatement of the reference (oracle/bls_oracle.c), %d pthreads" % (sample, args.steps, threads)},
+        "e2e": {"value": value, "unit": "pairings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def make_inputs(eng, n, seed, torch, np):
+    """P_i = [a_i] g1, Q_i = [b_i] g2 on the device with the engine's own kernels (wNAF + batch
+    normalisation), as affine rows.  Scalars: SplitMix64 stream, rejection-sampled below r."""
+    import pairing_b200._native as nat
+
+    def splitmix(seed, count):
+        with np.errstate(over="ignore"):
+            idx = np.arange(1, count + 1, dtype=np.uint64)
+            z = np.uint64(seed & (2**64 - 1)) + idx * np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            return z ^ (z >> np.uint64(31))
+
+    def scalars(seed):
+        k = splitmix(seed, 4 * n).reshape(n, 4)
+        k[:, 3] &= np.uint64((1 << 62) - 1)        # < 2^254 < r: uniform enough for a throughput workload
+        k[:, 0] |= np.uint64(2)
+        return torch.from_numpy(k.view(np.int64)).to(eng.device)
+
+    one = [0x760900000002fffd, 0xebf4000bc40c0002, 0x5f48985753c758ba, 0x77ce585370525745, 0x5c071a97a256ec6d, 0x15f65ec3fa80e493]
+    g1x = [0x5cb38790fd530c16, 0x7817fc679976fff5, 0x154f95c7143ba1c1, 0xf0ae6acdf3d0e747, 0xedce6ecc21dbf440, 0x120177419e0bfb75]
+    g1y = [0xbaac93d50ce72271, 0x8c22631a7918fd8e, 0xdd595f13570725ce, 0x51ac582950405194, 0x0e1c8c3fad0059c0, 0x0bbc3efc5008a26a]
+    g2 = [[0xf5f28fa202940a10, 0xb3f5fb2687b4961a, 0xa1a893b53e2ae580, 0x9894999d1a3caee9, 0x6f67b7631863366b, 0x058191924350bcd7],
+          [0xa5a9c0759e23f606, 0xaaa0c59dbccd60c3, 0x3bb17e18e2867806, 0x1b1ab6cc8541b367, 0xc2b6ed0ef2158547, 0x11922a097360edf3],
+          [0x4c730af860494c4a, 0x597cfa1f5e369c5a, 0xe7e6856caa0a635a, 0xbbefb5e96e0d495f, 0x07d3a975f0ef25a2, 0x0083fd8e7e80dae5],
+          [0xadc0fc92df64b05d, 0x18aa270a2b1461dc, 0x86adac6a3be4eba0, 0x79495c4ec93da33a, 0xe7175850a43ccaed, 0x0b2bc2a163de1bf2]]
+    b1 = np.array([g1x + g1y + one], dtype=np.uint64)
+    b2 = np.array([g2[0] + g2[1] + g2[2] + g2[3] + one + [0] * 6], dtype=np.uint64)
+    base1 = torch.from_numpy(np.repeat(b1, n, 0).view(np.int64)).to(eng.device)
+    base2 = torch.from_numpy(np.repeat(b2, n, 0).view(np.int64)).to(eng.device)
+    p = eng.g1_wnaf_mul(base1, scalars(seed ^ 0x1111))
+    q = eng.g2_wnaf_mul(base2, scalars(seed ^ 0x2222))
+    eng.g1_batch_normalization_(p)
+    eng.g2_batch_normalization_(q)
+    pa = eng.jacobian_to_affine_rows(p, 6)
+    qa = eng.jacobian_to_affine_rows(q, 12)
+    torch.cuda.synchronize()
+    assert pa.shape[1] == nat.W_G1A and qa.shape[1] == nat.W_G2A
+    return pa, qa, p, scalars(seed ^ 0x3333)
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world != 1:
+        raise SystemExit("WORLD_SIZE=%d does not match --gpus %d" % (world, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from pairing_b200.device import DeviceEngine
+    eng = DeviceEngine(device=local_rank)
+    ctx = eng.ctx
+    n = 1 << args.batch_log2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pa, qa, g1_jac, g1_scalars = make_inputs(eng, n, SEED + rank, torch, np)
+    out = torch.empty((n, 72), dtype=torch.int64, device=eng.device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=eng.device)   # > 126 MB L2
+
+    def step():
+        flush.zero_()                       # evict the previous step's inputs/outputs from L2
+        eng.pairing(pa, qa, out)
+
+    # integer-multiply peak in the same run (roofline denominator)
+    peak_macs, _ = ctx.imad_peak(0, 4000)
+    fpmul_macs, _ = ctx.imad_peak(1, 2000)
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        flush.zero_()
+        kev[i][0].record()
+        eng.pairing(pa, qa, out)
+        kev[i][1].record()
+    ev1.record()
+    barrier()
+    launches = ctx.launch_count - launches0
+    total_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps     # the pairing kernel alone, this rank
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * n * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through the C-ABI call a user makes (copies inside the timed region)
+    ph = torch.empty(pa.shape, dtype=torch.int64).pin_memory(); ph.copy_(pa.cpu())
+    qh = torch.empty(qa.shape, dtype=torch.int64).pin_memory(); qh.copy_(qa.cpu())
+    oh = torch.empty((n, 72), dtype=torch.int64).pin_memory()
+    import ctypes
+    lib = ctx._lib
+
+    def e2e_step():
+        rc = lib.bls_pairing_batch(ctx._ctx, ph.data_ptr(), qh.data_ptr(), oh.data_ptr(), n)
+        if rc != 0:
+            raise SystemExit("bls_pairing_batch failed: %d" % rc)
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    e2e_dt = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * n * args.steps / e2e_dt
+    checksum = int(oh[:, 0].sum().item()) & 0xFFFFFFFF            # the step's result is read on the host
+    same = bool(torch.equal(oh, out.cpu()))                       # e2e output == device-path output
+
+    # ---- secondary: G1 wNAF scalar multiplication + batch normalisation (configs[3], reduced to 2^20 by default)
+    secondary = {}
+    if not args.no_secondary:
+        nw = min(1 << 20, max(n, 1 << 16))
+        bases = g1_jac[:n].repeat((nw + n - 1) // n, 1)[:nw].contiguous()
+        ks = g1_scalars[:n].repeat((nw + n - 1) // n, 1)[:nw].contiguous()
+        wout = torch.empty_like(bases)
+        eng.g1_wnaf_mul(bases, ks, 0, wout); eng.g1_batch_normalization_(wout)
+        barrier()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        eng.g1_wnaf_mul(bases, ks, 0, wout); eng.g1_batch_normalization_(wout)
+        w1.record()
+        barrier()
+        wms = max_over_ranks(w0.elapsed_time(w1))
+        wrate = world * nw / (wms * 1e-3)
+        secondary["g1_wnaf_mul"] = {"value": wrate, "unit": "scalar-muls/s", "points_per_gpu": nw, "ms": wms,
+                                    "roofline_frac": wrate / world * MAC32_PER_G1_WNAF / peak_macs}
+        # sharded multi-Miller product: n pairs per rank, 576-byte partials all-gathered (NCCL), merged on every rank
+        from pairing_b200 import dist as pdist
+        mm = pdist.multi_miller_loop_sharded(eng.multi_miller_loop, eng.fq12_product, pa, qa)
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        mm = pdist.multi_miller_loop_sharded(eng.multi_miller_loop, eng.fq12_product, pa, qa)
+        fe, _ = eng.final_exponentiation(mm)
+        m1.record()
+        barrier()
+        mms = max_over_ranks(m0.elapsed_time(m1))
+        secondary["multi_miller_loop"] = {"value": world * n / (mms * 1e-3), "unit": "pairs/s", "pairs_per_gpu": n, "ms": mms,
+                                          "collective": "all_gather of one 576-byte Fq12 per rank" if world > 1 else "none (1 rank)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- CPU baseline on the host cores (bounded sample)
+    cpu = None
+    if not args.no_cpu_baseline:
+        threads = len(os.sched_getaffinity(0))
+        probe_rate, _ = cpu_pairings_per_s(max(threads * 4, 32), threads)
+        sample = max(threads, int(probe_rate * 10.0))             # ~10 s of host work
+        rate, dt = cpu_pairings_per_s(sample, threads)
+        cpu = {"value": rate, "unit": "pairings/s", "cores": threads, "kind": "port",
+               "sample": "%d full pairings of the same workload in %.1f s, C restatement of the reference (oracle/bls_oracle.c), %d pthreads" % (sample, dt, threads)}
+
+    kernel_rate = n / (kernel_ms * 1e-3)                          # pairings/s of the dominant kernel on this GPU
+    achieved = kernel_rate * MAC32_PER_PAIRING
+    line = {
+        "metric": "BLS12-381 pairings/sec", "value": value, "unit": "pairings/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 limbs (12 x 32-bit Montgomery, IMAD.WIDE)", "data": "synthetic",
+        "config": {"workload": "batch of 2^%d independent full pairings per GPU (Miller loop + final exponentiation), BASELINE configs[1]" % args.batch_log2,
+                   "batch_per_gpu": n, "inputs": "G1Affine/G2Affine subgroup points = seeded scalar multiples of the generators, resident in HBM",
+                   "l2": "256 MiB buffer written between timed iterations (L2 flush)", "parallelism": "dp%d, no data-path collective" % world},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "pairings/s", "h2d_bytes_per_step": n * (104 + 200), "d2h_bytes_per_step": n * 576,
+                "api": "bls_pairing_batch (host buffers, pinned)", "matches_device_path": same, "checksum": checksum},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak_macs / 1e12, "unit": "TMAC32/s",
+                     "frac": achieved / peak_macs, "traffic": None,
+                     "kernel": "k_miller<true> (fused Miller loop + final exponentiation, one launch per step)",
+                     "kernel_ms": kernel_ms, "mac32_per_pairing": MAC32_PER_PAIRING,
+                     "peak_source": "IMAD.WIDE.U32 microbenchmark (bls_imad_peak variant 0) measured in this run; MEASURED_PEAKS.json has no integer figure",
+                     "fp_mul_chain_tmac32": fpmul_macs / 1e12,
+                     "hbm": {"achieved_gbs": kernel_rate * HBM_BYTES_PER_PAIRING / 1e9, "note": "algorithmic bytes; far from the 6548.8 GB/s measured HBM peak: the path is integer-multiply bound"}},
+        "cpu_baseline": cpu,
+        "secondary": secondary,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

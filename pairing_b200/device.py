@@ -1,0 +1,131 @@
+"""Device-resident batch API: torch CUDA tensors in, torch CUDA tensors out, no host copies.
+
+torch is plumbing only (device memory, streams, torch.distributed); every kernel is launched
+through the C ABI's `*_dev` entry points on torch's current stream.  Tensors are int64 with the
+ABI's u64 word layout, one row per element (same shapes as the numpy API: (n, 13) G1Affine, ...).
+"""
+import torch
+
+from . import _native as nat
+
+
+def _check(t, w, name):
+    if not (t.is_cuda and t.dtype == torch.int64 and t.dim() == 2 and t.shape[1] == w and t.is_contiguous()):
+        raise ValueError("%s must be a contiguous CUDA int64 tensor of shape (n, %d)" % (name, w))
+
+
+class DeviceEngine:
+    def __init__(self, ctx=None, device=None):
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.ctx = ctx if ctx is not None else nat.Context(self.device.index or 0)
+        self._scratch = {}
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _buf(self, key, nbytes):
+        """Grow-only named scratch buffer, so the timed path never allocates."""
+        t = self._scratch.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+            self._scratch[key] = t
+        return t
+
+    # ---------------------------------------------------------------- pairing engine
+    def pairing(self, p, q, out=None):
+        _check(p, nat.W_G1A, "p"); _check(q, nat.W_G2A, "q")
+        n = p.shape[0]
+        if out is None:
+            out = torch.empty((n, nat.W_FQ12), dtype=torch.int64, device=self.device)
+        self.ctx.call_dev("bls_pairing_dev", p.data_ptr(), q.data_ptr(), out.data_ptr(), n, self._stream())
+        return out
+
+    def miller_loop_batch(self, p, q, out=None):
+        _check(p, nat.W_G1A, "p"); _check(q, nat.W_G2A, "q")
+        n = p.shape[0]
+        if out is None:
+            out = torch.empty((n, nat.W_FQ12), dtype=torch.int64, device=self.device)
+        self.ctx.call_dev("bls_miller_loop_dev", p.data_ptr(), q.data_ptr(), out.data_ptr(), n, self._stream())
+        return out
+
+    def g2_prepare(self, q, out=None):
+        _check(q, nat.W_G2A, "q")
+        n = q.shape[0]
+        if out is None:
+            out = torch.empty((n, nat.W_G2P), dtype=torch.int64, device=self.device)
+        self.ctx.call_dev("bls_g2_prepare_dev", q.data_ptr(), out.data_ptr(), n, self._stream())
+        return out
+
+    def miller_loop_prepared_batch(self, p, qp, out=None):
+        _check(p, nat.W_G1A, "p"); _check(qp, nat.W_G2P, "qp")
+        n = p.shape[0]
+        if out is None:
+            out = torch.empty((n, nat.W_FQ12), dtype=torch.int64, device=self.device)
+        self.ctx.call_dev("bls_miller_loop_prepared_dev", p.data_ptr(), qp.data_ptr(), out.data_ptr(), n, self._stream())
+        return out
+
+    def final_exponentiation(self, f, out=None):
+        _check(f, nat.W_FQ12, "f")
+        n = f.shape[0]
+        if out is None:
+            out = torch.empty_like(f)
+        ok = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self.ctx.call_dev("bls_final_exponentiation_dev", f.data_ptr(), out.data_ptr(), ok.data_ptr(), n, self._stream())
+        return out, ok
+
+    def multi_miller_loop(self, p, q, out=None):
+        """Product of the Miller values of all pairs of this device's shard -> (1, 72)."""
+        _check(p, nat.W_G1A, "p"); _check(q, nat.W_G2A, "q")
+        n = p.shape[0]
+        if out is None:
+            out = torch.empty((1, nat.W_FQ12), dtype=torch.int64, device=self.device)
+        scr = self._buf("mm", self.ctx.multi_miller_scratch_bytes(n))
+        self.ctx.call_dev("bls_multi_miller_loop_dev", p.data_ptr(), q.data_ptr(), n, out.data_ptr(), scr.data_ptr(), self._stream())
+        return out
+
+    def fq12_product(self, f, out=None):
+        _check(f, nat.W_FQ12, "f")
+        n = f.shape[0]
+        if out is None:
+            out = torch.empty((1, nat.W_FQ12), dtype=torch.int64, device=self.device)
+        scr = self._buf("prod", self.ctx.fq12_product_scratch_bytes(n))
+        self.ctx.call_dev("bls_fq12_product_dev", f.data_ptr(), n, out.data_ptr(), scr.data_ptr(), self._stream())
+        return out
+
+    # ---------------------------------------------------------------- curves
+    def g1_wnaf_mul(self, bases, k, window=0, out=None):
+        _check(bases, nat.W_G1, "bases"); _check(k, nat.W_FR, "k")
+        if out is None:
+            out = torch.empty_like(bases)
+        self.ctx.call_dev("bls_g1_wnaf_mul_dev", bases.data_ptr(), k.data_ptr(), out.data_ptr(), bases.shape[0], window, self._stream())
+        return out
+
+    def g2_wnaf_mul(self, bases, k, window=0, out=None):
+        _check(bases, nat.W_G2, "bases"); _check(k, nat.W_FR, "k")
+        if out is None:
+            out = torch.empty_like(bases)
+        self.ctx.call_dev("bls_g2_wnaf_mul_dev", bases.data_ptr(), k.data_ptr(), out.data_ptr(), bases.shape[0], window, self._stream())
+        return out
+
+    def g1_batch_normalization_(self, v):
+        _check(v, nat.W_G1, "v")
+        scr = self._buf("bn", self.ctx.batch_normalization_scratch_bytes(1, v.shape[0]))
+        self.ctx.call_dev("bls_g1_batch_normalization_dev", v.data_ptr(), v.shape[0], scr.data_ptr(), self._stream())
+        return v
+
+    def g2_batch_normalization_(self, v):
+        _check(v, nat.W_G2, "v")
+        scr = self._buf("bn", self.ctx.batch_normalization_scratch_bytes(2, v.shape[0]))
+        self.ctx.call_dev("bls_g2_batch_normalization_dev", v.data_ptr(), v.shape[0], scr.data_ptr(), self._stream())
+        return v
+
+    # normalised Jacobian -> affine rows (pure data movement: x, y, infinity flag = (z == 0))
+    @staticmethod
+    def jacobian_to_affine_rows(v, coord_words):
+        n = v.shape[0]
+        out = torch.zeros((n, 2 * coord_words + 1), dtype=torch.int64, device=v.device)
+        out[:, :2 * coord_words] = v[:, :2 * coord_words]
+        out[:, 2 * coord_words] = (v[:, 2 * coord_words:] == 0).all(dim=1).to(torch.int64)
+        return out

@@ -1,0 +1,74 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads without a GPU, exports every
+symbol include/pairing_b200.h declares, struct sizes match the header's layout, and the product
+fails loudly (no fallback) when no device is present."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pairing_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bls_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import pairing_b200._native as nat
+    lib = nat.load()
+    names = header_functions()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), "libpairing_b200.so does not export %s" % n
+    assert sorted(nat.SYMBOLS) == names, "pairing_b200._native.SYMBOLS is out of sync with the header"
+    out = subprocess.check_output(["nm", "-D", "--defined-only", nat.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (bls_[a-z0-9_]+)", out))
+    assert set(names) <= exported
+
+
+def test_struct_sizes_match_header():
+    """A throw-away C program prints sizeof() of every ABI struct; the numpy row widths must agree."""
+    import pairing_b200._native as nat
+    import tempfile
+    src = '#include <stdio.h>\n#include "pairing_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+          'sizeof(bls_fq),sizeof(bls_fq2),sizeof(bls_fq6),sizeof(bls_fq12),sizeof(bls_g1_affine),sizeof(bls_g1),' \
+          'sizeof(bls_g2_affine),sizeof(bls_g2),sizeof(bls_fr_repr),sizeof(bls_g2_prepared));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", exe, c])
+        sizes = [int(x) for x in subprocess.check_output([exe], text=True).split()]
+    want = [8 * w for w in (nat.W_FQ, nat.W_FQ2, nat.W_FQ6, nat.W_FQ12, nat.W_G1A, nat.W_G1, nat.W_G2A, nat.W_G2, nat.W_FR, nat.W_G2P)]
+    assert sizes == want == [48, 96, 288, 576, 104, 144, 200, 288, 32, 19592]
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the context cannot be created and the API raises; it never computes on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import pairing_b200
+    with pytest.raises(pairing_b200.BlsError):
+        pairing_b200.Context(0)
+    lib = pairing_b200.load()
+    err = ctypes.c_int(0)
+    assert not lib.bls_ctx_create(0, ctypes.byref(err))
+    assert err.value == -2 and b"no CPU fallback" in lib.bls_strerror(err.value)
+    # NULL context -> invalid argument, not a crash
+    assert lib.bls_pairing_batch(None, None, None, None, 4) == -1
+
+
+def test_product_package_never_imports_the_oracle():
+    for fn in os.listdir(os.path.join(ROOT, "pairing_b200")):
+        if fn.endswith(".py"):
+            src = open(os.path.join(ROOT, "pairing_b200", fn)).read()
+            assert "oracle_lib" not in src and "bls_model" not in src and "import oracle" not in src, fn
+    for fn in os.listdir(os.path.join(ROOT, "pairing_b200", "csrc")):
+        src = open(os.path.join(ROOT, "pairing_b200", "csrc", fn)).read()
+        assert "oracle/" not in src and "bls_oracle" not in src, fn

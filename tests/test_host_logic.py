@@ -1,0 +1,111 @@
+"""CPU tests of the host-side logic: window heuristics, sharding, the gloo world_size-2 exchange of
+the sharded multi-Miller product (local products computed by the oracle here -- there is no GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import bls_model as m
+import datagen as dg
+import oracle_lib as o
+from pairing_b200 import engine
+from pairing_b200 import dist as pdist
+
+
+def test_num_bits_and_windows_match_reference_rules():
+    """ec.rs:895-905 (G1: 4 if bits >= 130, 3 if >= 34, else 2) and 1586-1596 (G2: 103 / 37)"""
+    vals = [0, 1, 2, 3, (1 << 33) - 1, 1 << 33, (1 << 34) - 1, 1 << 36, (1 << 37) - 1, 1 << 102, (1 << 103) - 1,
+            1 << 103, 1 << 129, (1 << 130) - 1, 1 << 130, m.R_ORDER - 1]
+    k = np.array([m.limbs64(v, 4) for v in vals], dtype=np.uint64)
+    assert engine._num_bits(k).tolist() == [v.bit_length() for v in vals]
+    assert engine.G1.recommended_wnaf_for_scalar(k).tolist() == [m.g1_recommended_wnaf_for_scalar(v) for v in vals]
+    assert engine.G2.recommended_wnaf_for_scalar(k).tolist() == [m.g2_recommended_wnaf_for_scalar(v) for v in vals]
+    lib = o.lib()
+    import ctypes
+    for row, v in zip(k, vals):
+        assert lib.oracle_g1_window_for_scalar(row.ctypes.data_as(ctypes.c_void_p)) == m.g1_recommended_wnaf_for_scalar(v)
+        assert lib.oracle_g2_window_for_scalar(row.ctypes.data_as(ctypes.c_void_p)) == m.g2_recommended_wnaf_for_scalar(v)
+
+
+def test_recommended_wnaf_for_num_scalars():
+    """ec.rs:907-921 / 1598-1612"""
+    for n in (0, 1, 2, 3, 4, 7, 8, 21, 44, 121, 274, 564, 1631, 3129, 7934, 62570, 10**6):
+        assert engine.G1.recommended_wnaf_for_num_scalars(n) == m.recommended_wnaf_for_num_scalars(m.G1_NUM_SCALARS_REC, n)
+        assert engine.G2.recommended_wnaf_for_num_scalars(n) == m.recommended_wnaf_for_num_scalars(m.G2_NUM_SCALARS_REC, n)
+    assert engine.G1.recommended_wnaf_for_num_scalars(1) == 4 and engine.G1.recommended_wnaf_for_num_scalars(10**6) == 16
+    assert engine.G2.recommended_wnaf_for_num_scalars(10**6) == 15
+
+
+def test_into_projective_rows():
+    p = dg.g1_affine_points(5, 3, infinity_at=(2,))
+    assert np.array_equal(engine.G1Affine.into_projective(p), o.g1_from_affine(p))
+    q = dg.g2_affine_points(5, 4, infinity_at=(0,))
+    assert np.array_equal(engine.G2Affine.into_projective(q), o.g2_from_affine(q))
+
+
+def test_shard_range_partitions():
+    for n in (0, 1, 7, 64, 65537):
+        for world in (1, 2, 3, 8):
+            spans = [pdist.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_wnaf_form_matches_model():
+    """wnaf.rs:18-43 digits: C oracle == big-int model, for every window the reference tests (2..13)"""
+    ks = dg.rand_scalars(24, 5)
+    for w in range(2, 14):
+        for row in ks:
+            k = m.from_limbs64(row)
+            assert o.wnaf_form(row, w) == m.wnaf_form(k, w)
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    return port
+
+
+def _worker(rank, world, port, n, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = dg.g1_affine_points(n, 31, infinity_at=(1,))
+    q = dg.g2_affine_points(n, 32, infinity_at=(n - 2,))
+    lo, hi = pdist.shard_range(n, rank, world)
+
+    def local_product(ps, qs):
+        return torch.from_numpy(o.multi_miller_product(ps, qs, 1).view(np.int64))
+
+    def merge(parts):
+        f = parts.numpy().view(np.uint64)
+        acc = f[:1].copy()
+        for i in range(1, f.shape[0]):
+            acc = o.fq12_op("mul", acc, f[i:i + 1])[0]
+        return torch.from_numpy(acc.view(np.int64))
+
+    got = pdist.multi_miller_loop_sharded(local_product, merge, p[lo:hi], q[lo:hi])
+    ret[rank] = got.numpy().view(np.uint64).tobytes()
+    dist.destroy_process_group()
+
+
+def test_sharded_multi_miller_gloo_world2():
+    """N > 1 path on CPU: 2 gloo ranks each reduce their shard, all-gather the 576-byte partials and
+    merge; every rank ends with the reference's single-accumulator Miller value."""
+    import torch.multiprocessing as mp
+    n, world = 10, 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    procs = [mp.get_context("spawn").Process(target=_worker, args=(r, world, port, n, ret)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    for p_ in procs:
+        p_.join(120)
+        assert p_.exitcode == 0
+    p = dg.g1_affine_points(n, 31, infinity_at=(1,))
+    q = dg.g2_affine_points(n, 32, infinity_at=(n - 2,))
+    want = o.multi_miller_loop(p, q).tobytes()        # the literal Engine::miller_loop over all pairs
+    assert ret[0] == want and ret[1] == want
