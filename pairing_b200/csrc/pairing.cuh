@@ -86,17 +86,17 @@ __device__ __forceinline__ void miller_loop_single(Fp12& f, const Fp& px, const 
   fp12_conjugate(f);   // BLS_X_IS_NEGATIVE
 }
 
-// Field::pow(&[x]) for a 64-bit exponent (lib.rs:306-324) followed by the conjugation of
-// exp_by_x (mod.rs:116-121).
+// exp_by_x (mod.rs:116-121): Field::pow(&[x]) (lib.rs:306-324) followed by a conjugation.
+// Two value-preserving shortcuts (SURVEY.md 8c "latitude"): the leading `one * self` product of pow
+// is a copy, and -- the operand being in the cyclotomic subgroup (it is only called after the easy
+// part) -- every squaring is a Granger-Scott cyclotomic squaring.
 __device__ __noinline__ void fp12_exp_by_x(Fp12& out, const Fp12& a, uint64_t x) {
-  Fp12 res;
-  fp12_one(res);
-  bool found_one = false;
+  Fp12 res = a;
+  const int top = 63 - __clzll((long long)x);
 #pragma unroll 1
-  for (int n = 63; n >= 0; n--) {
-    bool bit = (x >> n) & 1ull;
-    if (found_one) fp12_sqr(res, res); else found_one = bit;
-    if (bit) fp12_mul(res, res, a);
+  for (int n = top - 1; n >= 0; n--) {
+    fp12_cyclotomic_sqr(res, res);
+    if ((x >> n) & 1ull) fp12_mul(res, res, a);
   }
   fp12_conjugate(res);
   out = res;

@@ -23,7 +23,10 @@ class DeviceEngine:
         self._scratch = {}
 
     def _stream(self):
-        return torch.cuda.current_stream(self.device).cuda_stream
+        # torch's default stream has handle 0, which the C ABI reads as "use the context's own stream";
+        # name the legacy default stream explicitly (cudaStreamLegacy == 0x1) so that the kernels are
+        # ordered with torch's events and collectives.
+        return torch.cuda.current_stream(self.device).cuda_stream or 1
 
     def _buf(self, key, nbytes):
         """Grow-only named scratch buffer, so the timed path never allocates."""
