@@ -15,6 +15,7 @@
 
 #include "../../include/pairing_b200.h"
 #include "pairing.cuh"
+#include "pair_tower.cuh"
 
 using namespace bls;
 
@@ -211,8 +212,11 @@ __global__ void __launch_bounds__(128) k_g2_prepare(const uint64_t* q, uint64_t*
 }
 
 // n independent single-pair Miller loops (+ optional final exponentiation = Engine::pairing)
+#ifndef BLS_MINB
+#define BLS_MINB 2
+#endif
 template <bool FINAL_EXP>
-__global__ void __launch_bounds__(128) k_miller(const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {
+__global__ void __launch_bounds__(128, BLS_MINB) k_miller(const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint64_t* pi = p + G1A_W * i;
@@ -228,6 +232,65 @@ __global__ void __launch_bounds__(128) k_miller(const uint64_t* p, const uint64_
     st_fp12(out + FQ12_W * i, g);
   } else {
     st_fp12(out + FQ12_W * i, f);
+  }
+}
+
+// ---- lane-pair kernels (pair_tower.cuh): two adjacent lanes per pairing, lane c owns coefficient c
+// of every Fq2.  Threads past the end of the batch recompute the last element (every lane has to
+// reach every shuffle) and skip the store.
+__device__ __forceinline__ P2 ld_p2(const uint64_t* p) { return P2{ld_fp(p + 6 * pair_c())}; }
+__device__ __forceinline__ void st_p2(uint64_t* p, const P2& a) { st_fp(p + 6 * pair_c(), a.v); }
+__device__ __forceinline__ void ld_p12(P12& r, const uint64_t* p) {
+  r.c0.c0 = ld_p2(p); r.c0.c1 = ld_p2(p + 12); r.c0.c2 = ld_p2(p + 24);
+  r.c1.c0 = ld_p2(p + 36); r.c1.c1 = ld_p2(p + 48); r.c1.c2 = ld_p2(p + 60);
+}
+__device__ __forceinline__ void st_p12(uint64_t* p, const P12& a) {
+  st_p2(p, a.c0.c0); st_p2(p + 12, a.c0.c1); st_p2(p + 24, a.c0.c2);
+  st_p2(p + 36, a.c1.c0); st_p2(p + 48, a.c1.c1); st_p2(p + 60, a.c1.c2);
+}
+
+// launch shape of the lane-pair kernels: BLS_PAIR_TPB threads per block, BLS_PAIR_MINB blocks per SM
+// (registers per thread <= 65536 / (TPB * MINB)).  Small blocks keep the tail of a 2^16 batch short.
+#ifndef BLS_PAIR_TPB
+#define BLS_PAIR_TPB 128
+#endif
+#ifndef BLS_PAIR_MINB
+#define BLS_PAIR_MINB 2
+#endif
+template <bool FINAL_EXP>
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller(const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = t >> 1;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  const uint64_t* pi = p + G1A_W * i;
+  const uint64_t* qi = q + G2A_W * i;
+  const bool live = pi[12] == 0 && qi[24] == 0;
+  Fp px = ld_fp(pi), py = ld_fp(pi + 6);
+  P2 qx = ld_p2(qi), qy = ld_p2(qi + 12);
+  P12 f;
+  p_miller_loop_single(f, px, py, qx, qy);
+  if (!live) p12_one(f);                       // mod.rs:49-54: skipped pair, f stays one
+  if (FINAL_EXP) {
+    P12 g;
+    p_final_exponentiation(g, f);
+    if (active) st_p12(out + FQ12_W * i, g);
+  } else {
+    if (active) st_p12(out + FQ12_W * i, f);
+  }
+}
+
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_final_exp(const uint64_t* in, uint64_t* out, uint8_t* is_some, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = t >> 1;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  P12 f, g;
+  ld_p12(f, in + FQ12_W * i);
+  bool ok = p_final_exponentiation(g, f);
+  if (active) {
+    st_p12(out + FQ12_W * i, g);
+    if (is_some && pair_c() == 0) is_some[i] = ok;
   }
 }
 
@@ -648,7 +711,7 @@ int bls_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affin
   if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   CK(cudaSetDevice(ctx->device));
-  k_miller<false><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  k_pair_miller<false><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
 }
@@ -664,7 +727,7 @@ int bls_final_exponentiation_dev(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out
   if (!ctx || (n && (!in || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   CK(cudaSetDevice(ctx->device));
-  k_final_exp<<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)in, (uint64_t*)out, is_some, n);
+  k_pair_final_exp<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)in, (uint64_t*)out, is_some, n);
   LAUNCH_CHECK();
   return BLS_OK;
 }
@@ -672,7 +735,7 @@ int bls_pairing_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q
   if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   CK(cudaSetDevice(ctx->device));
-  k_miller<true><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  k_pair_miller<true><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
 }

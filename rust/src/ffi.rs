@@ -1,0 +1,47 @@
+//! Raw bindings of include/pairing_b200.h.  POD mirrors are `#[repr(C)]`; the crate's own `Fq`,
+//! `G1Affine`, ... are NOT (`pub(crate)` fields, no repr), so `lib.rs` marshals explicitly.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)] #[derive(Copy, Clone)] pub struct bls_fq { pub l: [u64; 6] }
+#[repr(C)] #[derive(Copy, Clone)] pub struct bls_fq2 { pub c0: bls_fq, pub c1: bls_fq }
+#[repr(C)] #[derive(Copy, Clone)] pub struct bls_fq6 { pub c0: bls_fq2, pub c1: bls_fq2, pub c2: bls_fq2 }
+#[repr(C)] #[derive(Copy, Clone)] pub struct bls_fq12 { pub c0: bls_fq6, pub c1: bls_fq6 }
+#[repr(C)] #[derive(Copy, Clone)] pub struct bls_g1_affine { pub x: bls_fq, pub y: bls_fq, pub infinity: u64 }
+#[repr(C)] #[derive(Copy, Clone)] pub struct bls_g1 { pub x: bls_fq, pub y: bls_fq, pub z: bls_fq }
+#[repr(C)] #[derive(Copy, Clone)] pub struct bls_g2_affine { pub x: bls_fq2, pub y: bls_fq2, pub infinity: u64 }
+#[repr(C)] #[derive(Copy, Clone)] pub struct bls_g2 { pub x: bls_fq2, pub y: bls_fq2, pub z: bls_fq2 }
+#[repr(C)] #[derive(Copy, Clone)] pub struct bls_fr_repr { pub l: [u64; 4] }
+#[repr(C)] #[derive(Copy, Clone)] pub struct bls_g2_prepared { pub coeffs: [[bls_fq2; 3]; 68], pub infinity: u64 }
+pub enum bls_ctx {}
+
+pub const BLS_OK: c_int = 0;
+
+extern "C" {
+    pub fn bls_ctx_create(device: c_int, err: *mut c_int) -> *mut bls_ctx;
+    pub fn bls_ctx_destroy(ctx: *mut bls_ctx);
+    pub fn bls_strerror(status: c_int) -> *const c_char;
+    pub fn bls_ctx_last_error(ctx: *const bls_ctx) -> *const c_char;
+
+    pub fn bls_g2_prepare_batch(ctx: *mut bls_ctx, q: *const bls_g2_affine, out: *mut bls_g2_prepared, n: usize) -> c_int;
+    pub fn bls_miller_loop_batch(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_affine, out: *mut bls_fq12, n: usize) -> c_int;
+    pub fn bls_miller_loop_prepared_batch(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_prepared, out: *mut bls_fq12, n: usize) -> c_int;
+    pub fn bls_multi_miller_loop(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_affine, n: usize, out1: *mut bls_fq12) -> c_int;
+    pub fn bls_multi_miller_loop_prepared(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_prepared, n: usize, out1: *mut bls_fq12) -> c_int;
+    pub fn bls_final_exponentiation_batch(ctx: *mut bls_ctx, input: *const bls_fq12, out: *mut bls_fq12, is_some: *mut u8, n: usize) -> c_int;
+    pub fn bls_pairing_batch(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_affine, out: *mut bls_fq12, n: usize) -> c_int;
+    pub fn bls_fq12_product(ctx: *mut bls_ctx, input: *const bls_fq12, n: usize, out1: *mut bls_fq12) -> c_int;
+
+    pub fn bls_g1_wnaf_mul_batch(ctx: *mut bls_ctx, bases: *const bls_g1, k: *const bls_fr_repr, out: *mut bls_g1, n: usize) -> c_int;
+    pub fn bls_g2_wnaf_mul_batch(ctx: *mut bls_ctx, bases: *const bls_g2, k: *const bls_fr_repr, out: *mut bls_g2, n: usize) -> c_int;
+    pub fn bls_g1_wnaf_mul_window_batch(ctx: *mut bls_ctx, bases: *const bls_g1, k: *const bls_fr_repr, out: *mut bls_g1, n: usize, window: c_int) -> c_int;
+    pub fn bls_g2_wnaf_mul_window_batch(ctx: *mut bls_ctx, bases: *const bls_g2, k: *const bls_fr_repr, out: *mut bls_g2, n: usize, window: c_int) -> c_int;
+    pub fn bls_g1_mul_batch(ctx: *mut bls_ctx, bases: *const bls_g1, k: *const bls_fr_repr, out: *mut bls_g1, n: usize) -> c_int;
+    pub fn bls_g2_mul_batch(ctx: *mut bls_ctx, bases: *const bls_g2, k: *const bls_fr_repr, out: *mut bls_g2, n: usize) -> c_int;
+    pub fn bls_g1_batch_normalization(ctx: *mut bls_ctx, inout: *mut bls_g1, n: usize) -> c_int;
+    pub fn bls_g2_batch_normalization(ctx: *mut bls_ctx, inout: *mut bls_g2, n: usize) -> c_int;
+    pub fn bls_g1_into_affine_batch(ctx: *mut bls_ctx, input: *const bls_g1, out: *mut bls_g1_affine, n: usize) -> c_int;
+    pub fn bls_g2_into_affine_batch(ctx: *mut bls_ctx, input: *const bls_g2, out: *mut bls_g2_affine, n: usize) -> c_int;
+    pub fn bls_g1_op_batch(ctx: *mut bls_ctx, op: c_int, a: *const bls_g1, b: *const c_void, out: *mut bls_g1, n: usize) -> c_int;
+    pub fn bls_g2_op_batch(ctx: *mut bls_ctx, op: c_int, a: *const bls_g2, b: *const c_void, out: *mut bls_g2, n: usize) -> c_int;
+}

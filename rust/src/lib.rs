@@ -1,0 +1,123 @@
+//! Slice-level GPU entry points next to the `pairing` crate's scalar trait methods.
+//!
+//! This file lives INSIDE a fork of the crate (module `bls12_381::gpu`): the point fields are
+//! `pub(crate)` (src/bls12_381/ec.rs:15-17, 33-35), so marshalling needs crate visibility.  The
+//! scalar trait methods (`Engine::pairing`, `CurveProjective::mul_assign`, ...) stay as they are;
+//! callers with batches use the functions below.  One `Gpu` = one `bls_ctx`; it is `Send` and is
+//! wrapped in a `Mutex` because calls on a context must be serialised.
+//!
+//! Authored, not compiled here (no Rust toolchain in the build image) -- see INTEGRATION.md.
+pub mod ffi;
+
+use ffi::*;
+use pairing::bls12_381::{Fq12, FrRepr, G1Affine, G2Affine, G1, G2};
+use std::sync::Mutex;
+
+#[derive(Debug)]
+pub struct GpuError(pub i32, pub String);
+
+pub struct Gpu { ctx: Mutex<*mut bls_ctx> }
+unsafe impl Send for Gpu {}
+unsafe impl Sync for Gpu {}
+
+impl Gpu {
+    /// One context per CUDA device; there is no CPU fallback (fails without a device).
+    pub fn new(device: i32) -> Result<Gpu, GpuError> {
+        let mut err = 0;
+        let ctx = unsafe { bls_ctx_create(device, &mut err) };
+        if ctx.is_null() { return Err(GpuError(err, strerror(err))); }
+        Ok(Gpu { ctx: Mutex::new(ctx) })
+    }
+
+    /// `Bls12::pairing(p_i, q_i)` for every i (src/lib.rs:101-109).
+    pub fn pairing_batch(&self, p: &[G1Affine], q: &[G2Affine]) -> Result<Vec<Fq12>, GpuError> {
+        assert_eq!(p.len(), q.len());
+        let pp: Vec<bls_g1_affine> = p.iter().map(marshal::g1_affine).collect();
+        let qq: Vec<bls_g2_affine> = q.iter().map(marshal::g2_affine).collect();
+        let mut out = vec![marshal::FQ12_ZERO; p.len()];
+        let ctx = self.ctx.lock().unwrap();
+        check(unsafe { bls_pairing_batch(*ctx, pp.as_ptr(), qq.as_ptr(), out.as_mut_ptr(), p.len()) }, *ctx)?;
+        Ok(out.iter().map(marshal::fq12_back).collect())
+    }
+
+    /// `Bls12::miller_loop(&[(&p_0.prepare(), &q_0.prepare()), ...])`: one shared accumulator (mod.rs:40-102).
+    pub fn multi_miller_loop(&self, p: &[G1Affine], q: &[G2Affine]) -> Result<Fq12, GpuError> {
+        assert_eq!(p.len(), q.len());
+        let pp: Vec<bls_g1_affine> = p.iter().map(marshal::g1_affine).collect();
+        let qq: Vec<bls_g2_affine> = q.iter().map(marshal::g2_affine).collect();
+        let mut out = marshal::FQ12_ZERO;
+        let ctx = self.ctx.lock().unwrap();
+        check(unsafe { bls_multi_miller_loop(*ctx, pp.as_ptr(), qq.as_ptr(), p.len(), &mut out) }, *ctx)?;
+        Ok(marshal::fq12_back(&out))
+    }
+
+    /// `Bls12::final_exponentiation` per element; `None` where the input is zero (mod.rs:104-160).
+    pub fn final_exponentiation_batch(&self, f: &[Fq12]) -> Result<Vec<Option<Fq12>>, GpuError> {
+        let ff: Vec<bls_fq12> = f.iter().map(marshal::fq12).collect();
+        let mut out = vec![marshal::FQ12_ZERO; f.len()];
+        let mut some = vec![0u8; f.len()];
+        let ctx = self.ctx.lock().unwrap();
+        check(unsafe { bls_final_exponentiation_batch(*ctx, ff.as_ptr(), out.as_mut_ptr(), some.as_mut_ptr(), f.len()) }, *ctx)?;
+        Ok(out.iter().zip(some).map(|(v, s)| if s != 0 { Some(marshal::fq12_back(v)) } else { None }).collect())
+    }
+
+    /// `Wnaf::new().scalar(k_i).base(g_i)` per element (wnaf.rs:111-128, 158-164); Jacobian outputs are
+    /// the reference's exact (X, Y, Z) triples.
+    pub fn g1_wnaf_mul_batch(&self, bases: &[G1], k: &[FrRepr]) -> Result<Vec<G1>, GpuError> {
+        assert_eq!(bases.len(), k.len());
+        let bb: Vec<bls_g1> = bases.iter().map(marshal::g1).collect();
+        let kk: Vec<bls_fr_repr> = k.iter().map(|r| bls_fr_repr { l: r.0 }).collect();
+        let mut out = bb.clone();
+        let ctx = self.ctx.lock().unwrap();
+        check(unsafe { bls_g1_wnaf_mul_batch(*ctx, bb.as_ptr(), kk.as_ptr(), out.as_mut_ptr(), bb.len()) }, *ctx)?;
+        Ok(out.iter().map(marshal::g1_back).collect())
+    }
+
+    /// `G1::batch_normalization(&mut v)` (ec.rs:246-294).
+    pub fn g1_batch_normalization(&self, v: &mut [G1]) -> Result<(), GpuError> {
+        let mut vv: Vec<bls_g1> = v.iter().map(marshal::g1).collect();
+        let ctx = self.ctx.lock().unwrap();
+        check(unsafe { bls_g1_batch_normalization(*ctx, vv.as_mut_ptr(), vv.len()) }, *ctx)?;
+        for (dst, src) in v.iter_mut().zip(vv.iter()) { *dst = marshal::g1_back(src); }
+        Ok(())
+    }
+    // g2_wnaf_mul_batch, g2_batch_normalization, g2_prepare_batch, miller_loop_batch: same pattern.
+}
+
+impl Drop for Gpu {
+    fn drop(&mut self) { unsafe { bls_ctx_destroy(*self.ctx.lock().unwrap()) } }
+}
+
+fn strerror(e: i32) -> String {
+    unsafe { std::ffi::CStr::from_ptr(bls_strerror(e)).to_string_lossy().into_owned() }
+}
+fn check(rc: i32, ctx: *mut bls_ctx) -> Result<(), GpuError> {
+    if rc == BLS_OK { return Ok(()); }
+    let detail = unsafe { std::ffi::CStr::from_ptr(bls_ctx_last_error(ctx)).to_string_lossy().into_owned() };
+    Err(GpuError(rc, format!("{} [{}]", strerror(rc), detail)))
+}
+
+/// Explicit field-by-field copies between the crate's types and the `#[repr(C)]` mirrors.  `Fq` is
+/// `Fq(FqRepr([u64; 6]))` in Montgomery form (fq.rs:699-700), which is exactly `bls_fq`.
+mod marshal {
+    use super::ffi::*;
+    use pairing::bls12_381::*;
+    pub const FQ_ZERO: bls_fq = bls_fq { l: [0; 6] };
+    pub const FQ2_ZERO: bls_fq2 = bls_fq2 { c0: FQ_ZERO, c1: FQ_ZERO };
+    pub const FQ6_ZERO: bls_fq6 = bls_fq6 { c0: FQ2_ZERO, c1: FQ2_ZERO, c2: FQ2_ZERO };
+    pub const FQ12_ZERO: bls_fq12 = bls_fq12 { c0: FQ6_ZERO, c1: FQ6_ZERO };
+    // In the fork these use the crate-private accessors `Fq::mont_limbs()` / `Fq::from_mont_limbs()`
+    // (two one-line additions to fq.rs) so that no Montgomery conversion happens at the boundary.
+    pub fn fq(x: &Fq) -> bls_fq { bls_fq { l: x.mont_limbs() } }
+    pub fn fq_back(x: &bls_fq) -> Fq { Fq::from_mont_limbs(x.l) }
+    pub fn fq2(x: &Fq2) -> bls_fq2 { bls_fq2 { c0: fq(&x.c0), c1: fq(&x.c1) } }
+    pub fn fq2_back(x: &bls_fq2) -> Fq2 { Fq2 { c0: fq_back(&x.c0), c1: fq_back(&x.c1) } }
+    pub fn fq6(x: &Fq6) -> bls_fq6 { bls_fq6 { c0: fq2(&x.c0), c1: fq2(&x.c1), c2: fq2(&x.c2) } }
+    pub fn fq6_back(x: &bls_fq6) -> Fq6 { Fq6 { c0: fq2_back(&x.c0), c1: fq2_back(&x.c1), c2: fq2_back(&x.c2) } }
+    pub fn fq12(x: &Fq12) -> bls_fq12 { bls_fq12 { c0: fq6(&x.c0), c1: fq6(&x.c1) } }
+    pub fn fq12_back(x: &bls_fq12) -> Fq12 { Fq12 { c0: fq6_back(&x.c0), c1: fq6_back(&x.c1) } }
+    pub fn g1_affine(p: &G1Affine) -> bls_g1_affine { bls_g1_affine { x: fq(&p.x), y: fq(&p.y), infinity: p.infinity as u64 } }
+    pub fn g2_affine(p: &G2Affine) -> bls_g2_affine { bls_g2_affine { x: fq2(&p.x), y: fq2(&p.y), infinity: p.infinity as u64 } }
+    pub fn g1(p: &G1) -> bls_g1 { bls_g1 { x: fq(&p.x), y: fq(&p.y), z: fq(&p.z) } }
+    pub fn g1_back(p: &bls_g1) -> G1 { G1 { x: fq_back(&p.x), y: fq_back(&p.y), z: fq_back(&p.z) } }
+}
