@@ -343,7 +343,7 @@ def run_ours(args):
     line = {
         "metric": "BLS12-381 pairings/sec", "value": value, "unit": "pairings/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 1), "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u32 limbs (12 x 32-bit Montgomery, IMAD.WIDE)", "data": "synthetic",
+        "vs_baseline": None, "dtype": "u32 (12 x 32-bit Montgomery limbs, IMAD.WIDE.U32 carry chains)", "data": "synthetic",
         "config": {"workload": "batch of 2^%d independent full pairings per GPU (Miller loop + final exponentiation), BASELINE configs[1]" % args.batch_log2,
                    "batch_per_gpu": n, "inputs": "G1Affine/G2Affine subgroup points = seeded scalar multiples of the generators, resident in HBM",
                    "l2": "256 MiB buffer written between timed iterations (L2 flush)", "parallelism": "dp%d, no data-path collective" % world},
@@ -353,9 +353,9 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak_macs / 1e12, "unit": "TMAC32/s",
                      "frac": achieved / peak_macs, "traffic": None,
-                     "kernel": "k_miller<true> (fused Miller loop + final exponentiation, one launch per step)",
+                     "kernel": "k_pair_miller<true> (fused Miller loop + final exponentiation on lane pairs, one launch per step)",
                      "kernel_ms": kernel_ms, "mac32_per_pairing": MAC32_PER_PAIRING,
-                     "peak_source": "IMAD.WIDE.U32 microbenchmark (bls_imad_peak variant 0) measured in this run; MEASURED_PEAKS.json has no integer figure",
+                     "peak_source": "chain of dependent IMAD.WIDE.U32 (bls_imad_peak variant 0, SASS-checked by tests/test_abi.py) measured in this run: one 32x32->64 multiply per 4 cycles per SM sub-partition; MEASURED_PEAKS.json has no integer figure",
                      "fp_mul_chain_tmac32": fpmul_macs / 1e12,
                      "hbm": {"achieved_gbs": kernel_rate * HBM_BYTES_PER_PAIRING / 1e9, "note": "algorithmic bytes; far from the 6548.8 GB/s measured HBM peak: the path is integer-multiply bound"}},
         "cpu_baseline": cpu,

@@ -148,7 +148,8 @@ int bls_g2_batch_normalization_dev(bls_ctx*, bls_g2* inout, size_t n, void* scra
 
 /* ------------------------------------------------------------------ measurement
  * Register-resident integer-multiply microbenchmark: the roofline denominator for this path
- * (MEASURED_PEAKS.json has no integer figure).  variant 0 = independent IMAD.WIDE.U32 chains,
+ * (MEASURED_PEAKS.json has no integer figure).  variant 0 = chains of dependent IMAD.WIDE.U32
+ * (32x32->64, the only multiply in the loop -- checked on the SASS by tests/test_abi.py),
  * 1 = back-to-back fp_mul (300 MAC32 each), 2 = 32-bit IMAD, 3 = carry-linked
  * IMAD.WIDE.U32.X rows only (mad.lo.cc / madc.hi.cc chains, no reduction).
  * Returns multiply-accumulates per second in *macs_per_s and the kernel time in *ms. */

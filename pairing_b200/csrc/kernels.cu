@@ -545,24 +545,28 @@ __global__ void __launch_bounds__(128) k_batch_normalization(uint64_t* pts, size
 // ------------------------------------------------------------------------------------------------
 #define PEAK_CHAINS 8
 #define PEAK_UNROLL 32
+// 32x32->64 multiplies only: each chain squares its own 64-bit value, (lo, hi) <- lo * hi, so that both halves
+// of every product are consumed by the next multiply and nothing but IMAD.WIDE.U32 is left in the loop
+// (tests/test_abi.py disassembles the library and checks this).  A loop-invariant `mad.wide acc, a, b, acc`
+// is NOT a multiply benchmark: ptxas hoists a*b and the loop degenerates into 64-bit adds on the alu pipe.
 __global__ void __launch_bounds__(256) k_imad_wide_peak(uint32_t seed, int iters, uint64_t* sink) {
-  uint64_t acc[PEAK_CHAINS];
-  uint32_t a[PEAK_CHAINS];
+  uint32_t lo[PEAK_CHAINS], hi[PEAK_CHAINS];
   uint32_t b = seed ^ (threadIdx.x * 2654435761u);
 #pragma unroll
-  for (int k = 0; k < PEAK_CHAINS; k++) { acc[k] = seed + k; a[k] = b * (k + 3) + 1; }
+  for (int k = 0; k < PEAK_CHAINS; k++) { lo[k] = b * (2 * k + 3) + 1; hi[k] = (b ^ seed) + 77 * k; }
 #pragma unroll 1
   for (int it = 0; it < iters; it++) {
 #pragma unroll
     for (int u = 0; u < PEAK_UNROLL; u++) {
 #pragma unroll
-      for (int k = 0; k < PEAK_CHAINS; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a[k]), "r"(b));
+      for (int k = 0; k < PEAK_CHAINS; k++)
+        asm volatile("{.reg .u64 t; mul.wide.u32 t, %1, %0; mov.b64 {%0, %1}, t;}" : "+r"(lo[k]), "+r"(hi[k]));
     }
   }
-  uint64_t s = 0;
+  uint32_t s = 0;
 #pragma unroll
-  for (int k = 0; k < PEAK_CHAINS; k++) s ^= acc[k];
-  if (s == 0x1234567ull) sink[0] = s;
+  for (int k = 0; k < PEAK_CHAINS; k++) s ^= lo[k] ^ hi[k];
+  if (s == 0x1234567u) sink[0] = s;
 }
 __global__ void __launch_bounds__(256) k_imad32_peak(uint32_t seed, int iters, uint64_t* sink) {
   uint32_t acc[PEAK_CHAINS];

@@ -72,3 +72,40 @@ def test_product_package_never_imports_the_oracle():
     for fn in os.listdir(os.path.join(ROOT, "pairing_b200", "csrc")):
         src = open(os.path.join(ROOT, "pairing_b200", "csrc", fn)).read()
         assert "oracle/" not in src and "bls_oracle" not in src, fn
+
+
+def _sass_histogram(function_substr):
+    """opcode histogram of one kernel of the built library (cuobjdump -sass)"""
+    import collections
+    import shutil
+    import pairing_b200._native as nat
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.check_output([exe, "-sass", nat.LIB_PATH], text=True)
+    hist, on = collections.Counter(), False
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            on = function_substr in m.group(1)
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", line)
+        if on and m:
+            hist[m.group(1)] += 1
+    return hist
+
+
+def test_roofline_denominator_kernel_is_imad_wide_only():
+    """the integer-multiply peak is measured by a loop that is SASS-checked to contain only
+    IMAD.WIDE.  (A loop-invariant mad.wide is hoisted by ptxas and measures 64-bit adds instead.)"""
+    h = _sass_histogram("k_imad_wide_peak")
+    assert h["IMAD.WIDE.U32"] >= 256, h
+    other_math = sum(v for k, v in h.items() if k.startswith(("IADD3", "LOP3", "SHF", "IMAD.HI", "IMAD.MOV")) or k == "IMAD")
+    assert other_math <= 40, h          # prologue/epilogue only
+
+
+def test_montgomery_product_is_carry_linked_imad_wide():
+    """fp_mul (fq.rs:910-960 + 1037-1122) is 288 IMAD.WIDE.U32(.X) + 12 IMAD per product: two products in the loop body"""
+    h = _sass_histogram("k_fpmul_peak")
+    wide = h["IMAD.WIDE.U32"] + h["IMAD.WIDE.U32.X"] + h["IMAD.HI.U32"]
+    assert 2 * 288 <= wide <= 2 * 288 + 16, h
