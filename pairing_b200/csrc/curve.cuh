@@ -207,6 +207,59 @@ template <class F> __device__ __forceinline__ void pt_wnaf_mul(Jac<F>& out, cons
   out = result;
 }
 
+// The same computation with the warp's lanes DECOUPLED: every lane walks its own (double, add) sequence
+// -- for digit i from the top: a double once a non-zero digit has been seen, then an add/sub if digit i
+// is non-zero -- but the warp only ever executes one of the two group operations at a time.  Executing
+// both at every digit position (the SIMT reading of wnaf_exp) leaves 5/6 of the lanes idle in every
+// addition (density of non-zero digits for w = 4: 1/6), i.e. 42 % lane efficiency.  Here lanes that have
+// reached an addition wait until enough of their neighbours have too (|add| >= 3.3 |double| or nobody can
+// double); tools/wnaf_sched_sim.py gives 76 % for this rule on random 255-bit scalars.  Each lane still
+// performs exactly the reference's operation sequence on its own point, so the Jacobian triple is the
+// reference's bit for bit.  No shuffles inside: divergence is safe for F = Fp / Fp2.
+template <class F> __device__ __forceinline__ void pt_wnaf_mul_lazy(Jac<F>& out, const Jac<F>& base, const Scalar& k, int window,
+                                                               Jac<F>* table, int8_t* digits) {
+  const int tsize = 1 << (window - 1);
+  {
+    Jac<F> b = base, dbl = base;
+    pt_double(dbl);
+#pragma unroll 1
+    for (int i = 0; i < 8; i++) {          // lanes with smaller windows sit out (the last add of wnaf.rs:11-14 is unused)
+      if (i < tsize) { table[i] = b; if (i + 1 < tsize) pt_add(b, dbl); }
+    }
+  }
+  int i = wnaf_form(digits, k, window) - 1;
+  Jac<F> result;
+  pt_set_zero(result);
+  bool found_one = false, doubled = false;   // doubled: the double of position i has been done
+#pragma unroll 1
+  while (true) {
+    // next group operation of this lane: 0 = finished, 1 = double, 2 = add/sub of digit i
+    int op = 0, n = 0;
+#pragma unroll 1
+    while (i >= 0) {
+      if (found_one && !doubled) { op = 1; break; }
+      n = digits[i];
+      if (n != 0) { op = 2; break; }
+      i--; doubled = false;
+    }
+    const unsigned m_add = __ballot_sync(0xffffffffu, op == 2), m_dbl = __ballot_sync(0xffffffffu, op == 1);
+    if ((m_add | m_dbl) == 0) break;
+    const bool do_add = m_dbl == 0 || 3 * __popc(m_add) >= 10 * __popc(m_dbl);
+    if (do_add) {
+      if (op == 2) {
+        Jac<F> t = table[(n < 0 ? -n : n) >> 1];
+        if (n < 0) pt_negate(t);             // sub_assign: copy, negate, add (lib.rs:156-160)
+        pt_add(result, t);
+        found_one = true; doubled = false; i--;
+      }
+    } else if (op == 1) {
+      pt_double(result);
+      doubled = true;
+    }
+  }
+  out = result;
+}
+
 // double-and-add, ec.rs:534-553
 template <class F> __device__ __forceinline__ void pt_mul(Jac<F>& s, const Scalar& k) {
   Jac<F> res;

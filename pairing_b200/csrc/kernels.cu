@@ -337,58 +337,77 @@ __global__ void __launch_bounds__(128) k_final_exp(const uint64_t* in, uint64_t*
   if (is_some) is_some[i] = ok;
 }
 
-// Multi-pairing Miller loop (mod.rs:80-95): thread t owns pairs t, t+T, t+2T, ... and ONE accumulator
-// f shared by all of them, so the 62 Fq12 squarings are paid once per thread, not once per pair.
-// The running G2 points R_j live in a lane-interleaved scratch array (word-major, pair-minor) so that
-// a warp's loads/stores of one word are contiguous.  Each thread emits one partial product.
-__device__ __forceinline__ void ld_jac2_soa(Jac<Fp2>& r, const uint32_t* s, size_t n, size_t pair) {
+// Lane-pair form of the multi-pairing Miller loop (the production path of bls_multi_miller_loop*):
+// lane pair t owns pairs t, t+T, ... and ONE accumulator f.  Lane c keeps coefficient c of the running
+// G2 point R_j in the word-major scratch array: word k of pair j's coefficient c at rstate[(c*36+k)*n + j].
+// Every lane has to reach every shuffle, so there is no `continue`: a pair with an infinity member
+// (mod.rs:49-54) or past the end of the batch multiplies f by the sparse element (1, 0, 0) = one instead,
+// which leaves the canonical value of f unchanged.
+__device__ __forceinline__ void ld_pjac_soa(PJac& r, const uint32_t* s, size_t n, size_t pair) {
   uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+  const uint32_t* b = s + (size_t)pair_c() * 36 * n + pair;
 #pragma unroll
-  for (int k = 0; k < 72; k++) w[k] = s[(size_t)k * n + pair];
+  for (int k = 0; k < 36; k++) w[k] = b[(size_t)k * n];
 }
-__device__ __forceinline__ void st_jac2_soa(uint32_t* s, size_t n, size_t pair, const Jac<Fp2>& r) {
+__device__ __forceinline__ void st_pjac_soa(uint32_t* s, size_t n, size_t pair, const PJac& r) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
+  uint32_t* b = s + (size_t)pair_c() * 36 * n + pair;
 #pragma unroll
-  for (int k = 0; k < 72; k++) s[(size_t)k * n + pair] = w[k];
+  for (int k = 0; k < 36; k++) b[(size_t)k * n] = w[k];
+}
+__device__ __forceinline__ void pcoeffs_set_one_if(bool dead, PCoeffs& c) {
+  const P2 one = p2_one(), zero = p2_zero();
+  c.c0.v = fp_select(dead, zero.v, c.c0.v);
+  c.c1.v = fp_select(dead, zero.v, c.c1.v);
+  c.c2.v = fp_select(dead, one.v, c.c2.v);
 }
 
-__global__ void __launch_bounds__(128) k_multi_miller(const uint64_t* p, const uint64_t* q, size_t n, uint32_t* rstate, uint64_t* partials) {
-  const size_t T = (size_t)gridDim.x * blockDim.x;
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  Fp12 f;
-  fp12_one(f);
-  Coeffs c;
-  Jac<Fp2> r;
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_multi_miller(const uint64_t* p, const uint64_t* q, size_t n, uint32_t* rstate, uint64_t* partials) {
+  const size_t T = ((size_t)gridDim.x * blockDim.x) >> 1;                       // lane pairs
+  const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+  const size_t per = (n + T - 1) / T;                                            // loop trips, uniform over the grid
+  P12 f;
+  p12_one(f);
+  PCoeffs c;
+  PJac r;
 #pragma unroll 1
   for (int b = BLS_LOOP_TOP; b >= -1; b--) {   // b == -1 is the trailing doubling step (mod.rs:92-94)
     const bool bit = b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull);
 #pragma unroll 1
-    for (size_t i = t; i < n; i += T) {
+    for (size_t j = 0; j < per; j++) {
+      size_t i = t + j * T;
+      const bool in_range = i < n;
+      if (!in_range) i = n - 1;
       const uint64_t* pi = p + G1A_W * i;
       const uint64_t* qi = q + G2A_W * i;
-      if (pi[12] != 0 || qi[24] != 0) continue;   // pairs with an infinity member are skipped, mod.rs:49-54
-      if (b == BLS_LOOP_TOP) { r.x = ld_fp2(qi); r.y = ld_fp2(qi + 12); r.z = fp2_one(); }
-      else ld_jac2_soa(r, rstate, n, i);
-      g2_doubling_step(r, c);
-      ell(f, c, ld_fp(pi), ld_fp(pi + 6));
-      if (b >= 0) st_jac2_soa(rstate, n, i, r);
+      const bool dead = !in_range || pi[12] != 0 || qi[24] != 0;
+      if (b == BLS_LOOP_TOP) { r.x = ld_p2(qi); r.y = ld_p2(qi + 12); r.z = p2_one(); }
+      else ld_pjac_soa(r, rstate, n, i);
+      pg2_doubling_step(r, c);
+      pcoeffs_set_one_if(dead, c);
+      p_ell(f, c, ld_fp(pi), ld_fp(pi + 6));
+      if (b >= 0 && in_range) st_pjac_soa(rstate, n, i, r);
     }
     if (bit) {
 #pragma unroll 1
-      for (size_t i = t; i < n; i += T) {
+      for (size_t j = 0; j < per; j++) {
+        size_t i = t + j * T;
+        const bool in_range = i < n;
+        if (!in_range) i = n - 1;
         const uint64_t* pi = p + G1A_W * i;
         const uint64_t* qi = q + G2A_W * i;
-        if (pi[12] != 0 || qi[24] != 0) continue;
-        ld_jac2_soa(r, rstate, n, i);
-        g2_addition_step(r, ld_fp2(qi), ld_fp2(qi + 12), c);
-        ell(f, c, ld_fp(pi), ld_fp(pi + 6));
-        st_jac2_soa(rstate, n, i, r);
+        const bool dead = !in_range || pi[12] != 0 || qi[24] != 0;
+        ld_pjac_soa(r, rstate, n, i);
+        pg2_addition_step(r, ld_p2(qi), ld_p2(qi + 12), c);
+        pcoeffs_set_one_if(dead, c);
+        p_ell(f, c, ld_fp(pi), ld_fp(pi + 6));
+        if (in_range) st_pjac_soa(rstate, n, i, r);
       }
     }
-    if (b >= 0) fp12_sqr(f, f);
+    if (b >= 0) p12_sqr(f, f);
   }
-  fp12_conjugate(f);
-  st_fp12(partials + FQ12_W * t, f);
+  p12_conjugate(f);
+  st_p12(partials + FQ12_W * t, f);
 }
 
 __global__ void __launch_bounds__(128) k_multi_miller_prepared(const uint64_t* p, const uint64_t* qp, size_t n, uint64_t* partials) {
@@ -453,6 +472,35 @@ __global__ void __launch_bounds__(128) k_wnaf_mul(const uint64_t* bases, const u
   int8_t digits[260];
   pt_wnaf_mul(res, base, s, w, table, digits);
   st_jac(out + (size_t)PW * i, res);
+}
+
+// windows <= 4 (every window the per-scalar heuristics pick): lanes decoupled, see pt_wnaf_mul_lazy.
+// Threads past the end of the batch work on a zero scalar (they must reach the warp votes).
+#ifndef BLS_WNAF_MINB
+#define BLS_WNAF_MINB 3
+#endif
+template <class F, bool IS_G2>
+__global__ void __launch_bounds__(128, BLS_WNAF_MINB) k_wnaf_mul_lazy(const uint64_t* bases, const uint64_t* k, uint64_t* out, size_t n, int window) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  const int PW = 3 * FW<F>::W;
+  Jac<F> base, res;
+  ld_jac(base, bases + (size_t)PW * i);
+  Scalar s = ld_scalar(k + 4 * i);
+  if (!active) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) s.v[j] = 0;
+  }
+  int w = window;
+  if (w == 0) {
+    int nb = scalar_num_bits(s);
+    w = IS_G2 ? g2_window_for_bits(nb) : g1_window_for_bits(nb);
+  }
+  Jac<F> table[8];
+  int8_t digits[260];
+  pt_wnaf_mul_lazy(res, base, s, w, table, digits);
+  if (active) st_jac(out + (size_t)PW * i, res);
 }
 
 template <class F>
@@ -744,13 +792,21 @@ int bls_pairing_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q
   return BLS_OK;
 }
 
-// threads used by the multi-Miller kernel for n pairs: enough pairs per thread to amortise the
-// shared squarings, but never more threads than pairs
-static size_t mm_threads(const bls_ctx* ctx, size_t n) {
-  size_t full = (size_t)ctx->sm_count * 2 * TPB;   // 2 blocks of 128 per SM
+// threads (= partial products) of the thread-per-element multi-Miller kernel over prepared coefficients
+static size_t mm_threads_prepared(const bls_ctx* ctx, size_t n) {
+  size_t full = (size_t)ctx->sm_count * 2 * TPB;
   size_t t = n < full ? n : full;
   t = (t + TPB - 1) / TPB * TPB;
   return t ? t : TPB;
+}
+// lane pairs (= partial products) used by the multi-Miller kernel for n pairs: enough pairs per lane pair to
+// amortise the shared squarings, never more lane pairs than pairs; a multiple of the 64 lane pairs of a block
+static size_t mm_threads(const bls_ctx* ctx, size_t n) {
+  const size_t per_block = BLS_PAIR_TPB / 2;
+  size_t full = (size_t)ctx->sm_count * BLS_PAIR_MINB * per_block;
+  size_t t = n < full ? n : full;
+  t = (t + per_block - 1) / per_block * per_block;
+  return t ? t : per_block;
 }
 // product tree: a pass over `count` factors uses ceil(count/8) threads
 static size_t prod_threads(size_t count) { return count ? (count + 7) / 8 : 1; }
@@ -807,7 +863,7 @@ int bls_multi_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2
   uint32_t* rstate = (uint32_t*)scratch;
   uint64_t* partials = (uint64_t*)((char*)scratch + n * 72 * sizeof(uint32_t));
   uint64_t* prod_scratch = partials + T * FQ12_W;
-  k_multi_miller<<<(unsigned)(T / TPB), TPB, 0, s>>>((const uint64_t*)p, (const uint64_t*)q, n, rstate, partials);
+  k_pair_multi_miller<<<(unsigned)(2 * T / BLS_PAIR_TPB), BLS_PAIR_TPB, 0, s>>>((const uint64_t*)p, (const uint64_t*)q, n, rstate, partials);
   LAUNCH_CHECK();
   return product_passes(ctx, partials, T, out1, prod_scratch, s);
 }
@@ -816,7 +872,7 @@ int bls_g1_wnaf_mul_dev(bls_ctx* ctx, const bls_g1* bases, const bls_fr_repr* k,
   if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   CK(cudaSetDevice(ctx->device));
-  if (window <= 4) k_wnaf_mul<Fp, false, 8><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  if (window <= 4) k_wnaf_mul_lazy<Fp, false><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   else k_wnaf_mul<Fp, false, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   LAUNCH_CHECK();
   return BLS_OK;
@@ -825,7 +881,7 @@ int bls_g2_wnaf_mul_dev(bls_ctx* ctx, const bls_g2* bases, const bls_fr_repr* k,
   if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   CK(cudaSetDevice(ctx->device));
-  if (window <= 4) k_wnaf_mul<Fp2, true, 8><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  if (window <= 4) k_wnaf_mul_lazy<Fp2, true><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   else k_wnaf_mul<Fp2, true, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   LAUNCH_CHECK();
   return BLS_OK;
@@ -951,7 +1007,7 @@ int bls_multi_miller_loop_prepared(bls_ctx* ctx, const bls_g1_affine* p, const b
   CK(cudaSetDevice(ctx->device));
   H2D(dp, p, n * sizeof(*p));
   H2D(dq, q, n * sizeof(*q));
-  size_t T = mm_threads(ctx, n);
+  size_t T = mm_threads_prepared(ctx, n);
   DALLOC(dpart, T * sizeof(bls_fq12));
   DALLOC(dscr, bls_fq12_product_scratch_bytes(ctx, T));
   DALLOC(dout, sizeof(*out1));

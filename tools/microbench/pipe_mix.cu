@@ -93,6 +93,50 @@ template <class K> static void run(const char* name, K kern, int iters) {
   printf("%-44s %8.3f T op/s  (%.2f ms)  %.2f cyc/op/SMSP  %s\n", name, steps / best * 1e-9, best, cyc, cudaGetErrorString(cudaGetLastError()));
   cudaFree(sink);
 }
+
+template <class K> static void run_occ(const char* name, K kern, int iters, int threads, int blocks_per_sm) {
+  uint64_t* sink; cudaMalloc(&sink, 64);
+  int sm = 0; cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int r = 0; r < 4; r++) {
+    cudaEventRecord(a);
+    kern<<<sm * blocks_per_sm, threads>>>(12345u, iters, sink);
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (r && ms < best) best = ms;
+  }
+  double warps_per_smsp = threads / 32.0 * blocks_per_sm / 4.0;
+  double cyc = best * 1e-3 * 1.965e9 / ((double)NCH * UNR * iters * warps_per_smsp);
+  printf("%-40s %4d thr x %d blk/SM (%.1f warps/SMSP): %.2f cyc/op/SMSP\n", name, threads, blocks_per_sm, warps_per_smsp, cyc);
+  cudaFree(sink);
+}
+__global__ void __launch_bounds__(256) k_fpmul_chain(uint32_t seed, int iters, uint64_t* sink) {
+  Fp x = fp_one(), y = fp_r2();
+  x.v[0] ^= seed ^ threadIdx.x; y.v[1] ^= seed;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) { x = fp_mul_inline(x, y); y = fp_mul_inline(y, x); }
+  if (x.v[0] == 0x1234567u && y.v[3] == 7u) sink[0] = x.v[1];
+}
+__global__ void __launch_bounds__(256) k_fpmul2_chain(uint32_t seed, int iters, uint64_t* sink) {
+  Fp x = fp_one(), y = fp_r2(), z = fp_r2();
+  x.v[0] ^= seed ^ threadIdx.x; y.v[1] ^= seed; z.v[2] ^= seed;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) { x = fp_mul2_inline(x, y, z, x); y = fp_mul2_inline(y, x, z, y); }
+  if (x.v[0] == 0x1234567u && y.v[3] == 7u) sink[0] = x.v[1];
+}
+// two independent products per step (ILP 2)
+__global__ void __launch_bounds__(256) k_fpmul_ilp2(uint32_t seed, int iters, uint64_t* sink) {
+  Fp x = fp_one(), y = fp_r2(), u = fp_r2(), v = fp_one();
+  x.v[0] ^= seed ^ threadIdx.x; y.v[1] ^= seed; u.v[2] ^= threadIdx.x; v.v[3] ^= seed;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    Fp x2 = fp_mul_inline(x, y), u2 = fp_mul_inline(u, v);
+    y = fp_mul_inline(y, x2); v = fp_mul_inline(v, u2);
+    x = x2; u = u2;
+  }
+  if (x.v[0] == 0x1234567u && y.v[3] == 7u && u.v[1] == 5u && v.v[2] == 9u) sink[0] = x.v[1];
+}
 static float run_mix(int mode, int it_int, int it_dfma) {
   uint64_t* sink; cudaMalloc(&sink, 64);
   int sm = 0; cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, 0);
@@ -114,6 +158,11 @@ int main() {
   run("2 IMAD.HI.U32 (mul.hi)", k_rate<2>, 2000);
   run("3 IMAD.WIDE.U32 accumulate, no carry link", k_rate<3>, 2000);
   run("4 DFMA", k_rate<4>, 2000);
+  for (int thr : {128, 256, 384, 512}) run_occ("IMAD.WIDE.U32 chain x8", k_rate<0>, 2000, thr, 1);
+  // per fp_mul: iters*2 products of 300 MAC; report cycles per MAC: scale NCH*UNR=128 -> 600 MACs per iter
+  for (int thr : {128, 256, 384, 512}) run_occ("fp_mul chain (x 600/128 = cyc/MAC)", k_fpmul_chain, 500, thr, 1);
+  for (int thr : {128, 256, 384, 512}) run_occ("fp_mul2 chain (x 888/128)", k_fpmul2_chain, 500, thr, 1);
+  for (int thr : {128, 256, 384}) run_occ("fp_mul ilp2 (x 1200/128)", k_fpmul_ilp2, 500, thr, 1);
   // integer warps: 2*it_int fp_mul of 300 MAC32; fp64 warps: 128*it_dfma DFMA.  Balance so that each alone takes similar time.
   int it_int = 1000, it_dfma = 0;
   float t_int = run_mix(1, it_int, 0);
