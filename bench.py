@@ -12,7 +12,8 @@ per GPU (torchrun), every rank runs its own 2^16 batch (weak scaling, no data-pa
 The JSON line carries, besides the base contract: `roofline` (integer-multiply bound: algorithmic
 MAC32/s against the IMAD.WIDE peak measured in the same run), `cpu_baseline` (the C oracle timed on
 the host cores, rank 0, bounded sample), `e2e` (same metric through the host-buffer C-ABI call,
-copies inside the timed region), `secondary` (G1 wNAF muls/s and sharded multi-Miller pairs/s).
+copies inside the timed region), `secondary` (BASELINE configs[2..4] at their stated sizes: sharded multi-Miller pairs/s, G1 wNAF muls/s,
+G2 wNAF + G2Prepared).
 
 `--impl reference` times the reference's CPU algorithm (the C restatement in oracle/ -- the Rust
 crate cannot be built in this image) on all host threads, on a bounded sample per step.
@@ -32,6 +33,7 @@ BATCH_LOG2 = 16
 MAC32_PER_PAIRING = 20621 * 300          # 20 621 Fq mul/sq x 300 MAC32
 MAC32_PER_G1_WNAF = 2577 * 300           # wNAF w=4 mul + batch normalisation
 MAC32_PER_MM_PAIR = 4684 * 300           # multi-Miller per pair incl. on-the-fly prepare
+MAC32_PER_G2_WNAF_PREP = 7992 * 300      # G2 wNAF w=4 + normalisation + G2Prepared::from_affine
 HBM_BYTES_PER_PAIRING = 104 + 200 + 576  # G1Affine + G2Affine in, Fq12 out
 SEED = 0x5DBE62598D313D76
 
@@ -44,6 +46,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-log2", type=int, default=BATCH_LOG2)
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--mm-log2", type=int, default=20)
+    ap.add_argument("--wnaf-log2", type=int, default=24)
+    ap.add_argument("--g2-log2", type=int, default=20)
+    ap.add_argument("--prep-log2", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -291,37 +297,70 @@ def run_ours(args):
     checksum = int(oh[:, 0].sum().item()) & 0xFFFFFFFF            # the step's result is read on the host
     same = bool(torch.equal(oh, out.cpu()))                       # e2e output == device-path output
 
-    # ---- secondary: G1 wNAF scalar multiplication + batch normalisation (configs[3], reduced to 2^20 by default)
+    # ---- secondary: the other BASELINE configs at their stated sizes (one warm-up on a slice, one timed pass each;
+    # inputs are the 2^16 distinct points/scalars tiled to size -- the arithmetic does not depend on the values)
     secondary = {}
     if not args.no_secondary:
-        nw = min(1 << 20, max(n, 1 << 16))
-        bases = g1_jac[:n].repeat((nw + n - 1) // n, 1)[:nw].contiguous()
-        ks = g1_scalars[:n].repeat((nw + n - 1) // n, 1)[:nw].contiguous()
-        wout = torch.empty_like(bases)
-        eng.g1_wnaf_mul(bases, ks, 0, wout); eng.g1_batch_normalization_(wout)
-        barrier()
-        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0.record()
-        eng.g1_wnaf_mul(bases, ks, 0, wout); eng.g1_batch_normalization_(wout)
-        w1.record()
-        barrier()
-        wms = max_over_ranks(w0.elapsed_time(w1))
-        wrate = world * nw / (wms * 1e-3)
-        secondary["g1_wnaf_mul"] = {"value": wrate, "unit": "scalar-muls/s", "points_per_gpu": nw, "ms": wms,
-                                    "roofline_frac": wrate / world * MAC32_PER_G1_WNAF / peak_macs}
-        # sharded multi-Miller product: n pairs per rank, 576-byte partials all-gathered (NCCL), merged on every rank
+        def tile(t, m):
+            return t.repeat((m + t.shape[0] - 1) // t.shape[0], 1)[:m].contiguous()
+
+        def timed(fn):
+            barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record(); r = fn(); t1.record()
+            barrier()
+            return max_over_ranks(t0.elapsed_time(t1)), r
+
+        def entry(units, ms, mac_per_unit, **kw):
+            rate = world * units / (ms * 1e-3)
+            d = {"value": rate, "units_per_gpu": units, "ms": ms, "roofline_frac": rate / world * mac_per_unit / peak_macs}
+            d.update(kw)
+            return d
+
         from pairing_b200 import dist as pdist
-        mm = pdist.multi_miller_loop_sharded(eng.multi_miller_loop, eng.fq12_product, pa, qa)
-        barrier()
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m0.record()
-        mm = pdist.multi_miller_loop_sharded(eng.multi_miller_loop, eng.fq12_product, pa, qa)
-        fe, _ = eng.final_exponentiation(mm)
-        m1.record()
-        barrier()
-        mms = max_over_ranks(m0.elapsed_time(m1))
-        secondary["multi_miller_loop"] = {"value": world * n / (mms * 1e-3), "unit": "pairs/s", "pairs_per_gpu": n, "ms": mms,
-                                          "collective": "all_gather of one 576-byte Fq12 per rank" if world > 1 else "none (1 rank)"}
+        # configs[2]: multi_miller_loop product of 2^20 pairs per GPU + ONE shared final exponentiation
+        nm = 1 << args.mm_log2
+        pm, qm = tile(pa, nm), tile(qa, nm)
+        pdist.multi_miller_loop_sharded(eng.multi_miller_loop, eng.fq12_product, pm[:4096].contiguous(), qm[:4096].contiguous())
+        def mm_run():
+            mm = pdist.multi_miller_loop_sharded(eng.multi_miller_loop, eng.fq12_product, pm, qm)
+            return eng.final_exponentiation(mm)[0]
+        ms, fe = timed(mm_run)
+        secondary["multi_miller_loop"] = entry(nm, ms, MAC32_PER_MM_PAIR, unit="pairs/s",
+                                               collective="all_gather of one 576-byte Fq12 per rank (NCCL)" if world > 1 else "none (1 rank)",
+                                               config="configs[2]: product of 2^%d pairs per GPU, one final exponentiation" % args.mm_log2)
+        del pm, qm
+        # configs[3]: G1 wNAF scalar multiplication of 2^24 points per GPU + batch affine normalisation
+        nw = 1 << args.wnaf_log2
+        bases, ks = tile(g1_jac, nw), tile(g1_scalars, nw)
+        wout = torch.empty_like(bases)
+        eng.g1_batch_normalization_(eng.g1_wnaf_mul(bases[:4096].contiguous(), ks[:4096].contiguous(), 0))
+        ms_mul, _ = timed(lambda: eng.g1_wnaf_mul(bases, ks, 0, wout))
+        ms_norm, _ = timed(lambda: eng.g1_batch_normalization_(wout))
+        secondary["g1_wnaf_mul"] = entry(nw, ms_mul + ms_norm, MAC32_PER_G1_WNAF, unit="scalar-muls/s", ms_wnaf=ms_mul, ms_normalise=ms_norm,
+                                         config="configs[3]: 2^%d points x 255-bit scalars per GPU, wNAF w=4 + batch_normalization" % args.wnaf_log2)
+        del bases, ks, wout
+        # configs[4]: G2 wNAF scalar multiplication + batch normalisation + G2Prepared precomputation, 2^20 points per GPU
+        n2 = 1 << args.g2_log2
+        one = g1_jac[:1, 12:18]
+        q2 = torch.zeros((n, 36), dtype=torch.int64, device=eng.device)
+        q2[:, :24] = qa[:, :24]; q2[:, 24:30] = one
+        b2, k2 = tile(q2, n2), tile(g1_scalars, n2)
+        w2 = torch.empty_like(b2)
+        eng.g2_batch_normalization_(eng.g2_wnaf_mul(b2[:4096].contiguous(), k2[:4096].contiguous(), 0))
+        ms_mul, _ = timed(lambda: eng.g2_wnaf_mul(b2, k2, 0, w2))
+        ms_norm, _ = timed(lambda: eng.g2_batch_normalization_(w2))
+        aff2 = eng.jacobian_to_affine_rows(w2, 12)
+        del b2, k2, w2
+        npre = min(n2, 1 << args.prep_log2)
+        prep = torch.empty((npre, 68 * 36 + 1), dtype=torch.int64, device=eng.device)
+        eng.g2_prepare(aff2[:4096].contiguous(), prep[:4096])
+        ms_prep, _ = timed(lambda: eng.g2_prepare(aff2[:npre], prep))
+        ms_prep_full = ms_prep * n2 / npre
+        secondary["g2_wnaf_mul_prepare"] = entry(n2, ms_mul + ms_norm + ms_prep_full, MAC32_PER_G2_WNAF_PREP, unit="scalar-muls/s",
+                                                 ms_wnaf=ms_mul, ms_normalise=ms_norm, ms_prepare=ms_prep_full, prepared_points_timed=npre,
+                                                 config="configs[4]: 2^%d G2 points per GPU: wNAF w=4 + batch_normalization + G2Prepared (19 592 B per point)" % args.g2_log2)
+        del prep, aff2
 
     if rank != 0:
         if world > 1:
