@@ -377,6 +377,13 @@ def run_ours(args):
         cpu = {"value": rate, "unit": "pairings/s", "cores": threads, "kind": "port",
                "sample": "%d full pairings of the same workload in %.1f s, C restatement of the reference (oracle/bls_oracle.c), %d pthreads" % (sample, dt, threads)}
 
+    traffic = None                                                  # dram bytes per launch of the dominant kernel, from the committed ncu capture
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_pair_miller.json")))
+        if n == 1 << 16:
+            traffic = prof["traffic_bytes_per_launch"]
+    except Exception:
+        pass
     kernel_rate = n / (kernel_ms * 1e-3)                          # pairings/s of the dominant kernel on this GPU
     achieved = kernel_rate * MAC32_PER_PAIRING
     line = {
@@ -391,7 +398,8 @@ def run_ours(args):
                 "api": "bls_pairing_batch (host buffers, pinned)", "matches_device_path": same, "checksum": checksum},
         "gpu_launches": int(launches),
         "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak_macs / 1e12, "unit": "TMAC32/s",
-                     "frac": achieved / peak_macs, "traffic": None,
+                     "frac": achieved / peak_macs, "traffic": traffic,
+                     "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of profiles/r1_pair_miller.md; mostly local-memory (spill) write-back, 50 GB/s",
                      "kernel": "k_pair_miller<true> (fused Miller loop + final exponentiation on lane pairs, one launch per step)",
                      "kernel_ms": kernel_ms, "mac32_per_pairing": MAC32_PER_PAIRING,
                      "peak_source": "chain of dependent IMAD.WIDE.U32 (bls_imad_peak variant 0, SASS-checked by tests/test_abi.py) measured in this run: one 32x32->64 multiply per 4 cycles per SM sub-partition; MEASURED_PEAKS.json has no integer figure",
