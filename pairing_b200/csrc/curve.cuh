@@ -207,57 +207,61 @@ template <class F> __device__ __forceinline__ void pt_wnaf_mul(Jac<F>& out, cons
   out = result;
 }
 
-// The same computation with the warp's lanes DECOUPLED: every lane walks its own (double, add) sequence
-// -- for digit i from the top: a double once a non-zero digit has been seen, then an add/sub if digit i
-// is non-zero -- but the warp only ever executes one of the two group operations at a time.  Executing
-// both at every digit position (the SIMT reading of wnaf_exp) leaves 5/6 of the lanes idle in every
-// addition (density of non-zero digits for w = 4: 1/6), i.e. 42 % lane efficiency.  Here lanes that have
-// reached an addition wait until enough of their neighbours have too (|add| >= 3.3 |double| or nobody can
-// double); tools/wnaf_sched_sim.py gives 76 % for this rule on random 255-bit scalars.  Each lane still
-// performs exactly the reference's operation sequence on its own point, so the Jacobian triple is the
-// reference's bit for bit.  No shuffles inside: divergence is safe for F = Fp / Fp2.
-template <class F> __device__ __forceinline__ void pt_wnaf_mul_lazy(Jac<F>& out, const Jac<F>& base, const Scalar& k, int window,
-                                                               Jac<F>* table, int8_t* digits) {
-  const int tsize = 1 << (window - 1);
-  {
-    Jac<F> b = base, dbl = base;
-    pt_double(dbl);
-#pragma unroll 1
-    for (int i = 0; i < 8; i++) {          // lanes with smaller windows sit out (the last add of wnaf.rs:11-14 is unused)
-      if (i < tsize) { table[i] = b; if (i + 1 < tsize) pt_add(b, dbl); }
-    }
-  }
-  int i = wnaf_form(digits, k, window) - 1;
-  Jac<F> result;
-  pt_set_zero(result);
-  bool found_one = false, doubled = false;   // doubled: the double of position i has been done
+// wnaf_exp with the warp's lanes DECOUPLED: every lane walks its own (double, add) sequence -- for digit i
+// from the top: a double once a non-zero digit has been seen, then an add/sub if digit i is non-zero -- but
+// the warp only ever executes one of the two group operations at a time.  Executing both at every digit
+// position (the SIMT reading of wnaf_exp) leaves 5/6 of the lanes idle in every addition (density of
+// non-zero digits for w = 4: 1/6), i.e. 42 % lane efficiency.  Here lanes that have reached an addition wait
+// until enough of their neighbours have too.  Each lane still performs exactly the reference's operation
+// sequence on its own point, so the Jacobian triple is the reference's bit for bit.  No shuffles inside:
+// divergence is safe for F = Fp / Fp2.
+// K points per lane: a lane that has reached an addition on one of its points keeps doubling another one,
+// so it is almost never idle (tools/wnaf_sched_sim.py: 76 % lane efficiency for K = 1, 91 % for K = 2,
+// 95 % for K = 3).  Per point the operation sequence is still exactly the reference's.
+template <int K> struct WnafState {
+  int i[K];            // current digit position of point j (-1: finished)
+  bool found[K];       // a non-zero digit has been consumed (wnaf.rs:52, found_one)
+  bool doubled[K];     // the double of position i[j] has been done
+};
+template <class F, int K> __device__ __forceinline__ void pt_wnaf_run_lazy(Jac<F> (&res)[K], Jac<F> (&table)[K][8], int8_t (&digits)[K][260], WnafState<K>& st) {
 #pragma unroll 1
   while (true) {
-    // next group operation of this lane: 0 = finished, 1 = double, 2 = add/sub of digit i
-    int op = 0, n = 0;
+    // next group operation of every point of this lane: 0 = finished, 1 = double, 2 = add/sub of digit i
+    int op[K], dig[K];
+    bool has_add = false, has_dbl = false;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      op[j] = 0; dig[j] = 0;
 #pragma unroll 1
-    while (i >= 0) {
-      if (found_one && !doubled) { op = 1; break; }
-      n = digits[i];
-      if (n != 0) { op = 2; break; }
-      i--; doubled = false;
-    }
-    const unsigned m_add = __ballot_sync(0xffffffffu, op == 2), m_dbl = __ballot_sync(0xffffffffu, op == 1);
-    if ((m_add | m_dbl) == 0) break;
-    const bool do_add = m_dbl == 0 || 3 * __popc(m_add) >= 10 * __popc(m_dbl);
-    if (do_add) {
-      if (op == 2) {
-        Jac<F> t = table[(n < 0 ? -n : n) >> 1];
-        if (n < 0) pt_negate(t);             // sub_assign: copy, negate, add (lib.rs:156-160)
-        pt_add(result, t);
-        found_one = true; doubled = false; i--;
+      while (st.i[j] >= 0) {
+        if (st.found[j] && !st.doubled[j]) { op[j] = 1; break; }
+        dig[j] = digits[j][st.i[j]];
+        if (dig[j] != 0) { op[j] = 2; break; }
+        st.i[j]--; st.doubled[j] = false;
       }
-    } else if (op == 1) {
-      pt_double(result);
-      doubled = true;
+      has_add |= op[j] == 2; has_dbl |= op[j] == 1;
+    }
+    const unsigned m_add = __ballot_sync(0xffffffffu, has_add), m_dbl = __ballot_sync(0xffffffffu, has_dbl);
+    if ((m_add | m_dbl) == 0) break;
+    const bool do_add = m_dbl == 0 || (K == 1 ? 3 * __popc(m_add) >= 10 * __popc(m_dbl) : 4 * __popc(m_add) >= 5 * __popc(m_dbl));
+    // the point of this lane that wants the chosen operation and is furthest behind
+    int pick = -1, best = -1;
+#pragma unroll
+    for (int j = 0; j < K; j++)
+      if (op[j] == (do_add ? 2 : 1) && st.i[j] > best) { best = st.i[j]; pick = j; }
+    if (pick >= 0) {
+      if (do_add) {
+        const int n = dig[pick];
+        Jac<F> t = table[pick][(n < 0 ? -n : n) >> 1];
+        if (n < 0) pt_negate(t);             // sub_assign: copy, negate, add (lib.rs:156-160)
+        pt_add(res[pick], t);
+        st.found[pick] = true; st.doubled[pick] = false; st.i[pick]--;
+      } else {
+        pt_double(res[pick]);
+        st.doubled[pick] = true;
+      }
     }
   }
-  out = result;
 }
 
 // double-and-add, ec.rs:534-553

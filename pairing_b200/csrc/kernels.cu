@@ -474,33 +474,60 @@ __global__ void __launch_bounds__(128) k_wnaf_mul(const uint64_t* bases, const u
   st_jac(out + (size_t)PW * i, res);
 }
 
-// windows <= 4 (every window the per-scalar heuristics pick): lanes decoupled, see pt_wnaf_mul_lazy.
-// Threads past the end of the batch work on a zero scalar (they must reach the warp votes).
 #ifndef BLS_WNAF_MINB
 #define BLS_WNAF_MINB 3
 #endif
-template <class F, bool IS_G2>
-__global__ void __launch_bounds__(128, BLS_WNAF_MINB) k_wnaf_mul_lazy(const uint64_t* bases, const uint64_t* k, uint64_t* out, size_t n, int window) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = i < n;
-  if (!active) i = n - 1;
+// K points per thread (pt_wnaf_run_lazy): thread t owns points t, t + T, ..., t + (K-1) T
+#ifndef BLS_WNAF_K
+#define BLS_WNAF_K 2
+#endif
+#ifndef BLS_WNAF_K_G2
+#define BLS_WNAF_K_G2 2
+#endif
+// blocks per SM: 4 for G1 (128 registers), 3 for G2 (168) -- measured at 2^20 points: 9.17 vs 9.01 M G1 muls/s, 3.30 vs 2.90 M G2 muls/s
+template <class F, bool IS_G2, int K>
+__global__ void __launch_bounds__(128, IS_G2 ? BLS_WNAF_MINB : BLS_WNAF_MINB + 1) k_wnaf_mul_lazyk(const uint64_t* bases, const uint64_t* k, uint64_t* out, size_t n, int window) {
+  const size_t T = (size_t)gridDim.x * blockDim.x;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int PW = 3 * FW<F>::W;
-  Jac<F> base, res;
-  ld_jac(base, bases + (size_t)PW * i);
-  Scalar s = ld_scalar(k + 4 * i);
-  if (!active) {
+  Jac<F> res[K];
+  Jac<F> table[K][8];
+  int8_t digits[K][260];
+  WnafState<K> st;
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    size_t i = t + (size_t)j * T;
+    const bool active = i < n;
+    if (!active) i = n - 1;
+    Jac<F> base;
+    ld_jac(base, bases + (size_t)PW * i);
+    Scalar s = ld_scalar(k + 4 * i);
+    if (!active) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) s.v[j] = 0;
+      for (int w = 0; w < 8; w++) s.v[w] = 0;
+    }
+    int w = window;
+    if (w == 0) {
+      int nb = scalar_num_bits(s);
+      w = IS_G2 ? g2_window_for_bits(nb) : g1_window_for_bits(nb);
+    }
+    const int tsize = 1 << (w - 1);
+    Jac<F> b = base, dbl = base;
+    pt_double(dbl);
+#pragma unroll 1
+    for (int e = 0; e < 8; e++) {          // wnaf_table, wnaf.rs:4-15 (the last add is unused)
+      if (e < tsize) { table[j][e] = b; if (e + 1 < tsize) pt_add(b, dbl); }
+    }
+    st.i[j] = wnaf_form(digits[j], s, w) - 1;
+    st.found[j] = false; st.doubled[j] = false;
+    pt_set_zero(res[j]);
   }
-  int w = window;
-  if (w == 0) {
-    int nb = scalar_num_bits(s);
-    w = IS_G2 ? g2_window_for_bits(nb) : g1_window_for_bits(nb);
+  pt_wnaf_run_lazy<F, K>(res, table, digits, st);
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    size_t i = t + (size_t)j * T;
+    if (i < n) st_jac(out + (size_t)PW * i, res[j]);
   }
-  Jac<F> table[8];
-  int8_t digits[260];
-  pt_wnaf_mul_lazy(res, base, s, w, table, digits);
-  if (active) st_jac(out + (size_t)PW * i, res);
 }
 
 template <class F>
@@ -872,7 +899,7 @@ int bls_g1_wnaf_mul_dev(bls_ctx* ctx, const bls_g1* bases, const bls_fr_repr* k,
   if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   CK(cudaSetDevice(ctx->device));
-  if (window <= 4) k_wnaf_mul_lazy<Fp, false><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  if (window <= 4) k_wnaf_mul_lazyk<Fp, false, BLS_WNAF_K><<<blocks_for((n + BLS_WNAF_K - 1) / BLS_WNAF_K, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   else k_wnaf_mul<Fp, false, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   LAUNCH_CHECK();
   return BLS_OK;
@@ -881,7 +908,7 @@ int bls_g2_wnaf_mul_dev(bls_ctx* ctx, const bls_g2* bases, const bls_fr_repr* k,
   if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   CK(cudaSetDevice(ctx->device));
-  if (window <= 4) k_wnaf_mul_lazy<Fp2, true><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  if (window <= 4) k_wnaf_mul_lazyk<Fp2, true, BLS_WNAF_K_G2><<<blocks_for((n + BLS_WNAF_K_G2 - 1) / BLS_WNAF_K_G2, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   else k_wnaf_mul<Fp2, true, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   LAUNCH_CHECK();
   return BLS_OK;

@@ -81,7 +81,7 @@ if "g1" not in skip:
     report("G1 batch_normalization (+clone)", n, ms2, 7 * 300)
     report("G1 wNAF + normalisation", n, ms + ms2, 2577 * 300)
 if "g2" not in skip:
-    n2 = min(n, 1 << 17)
+    n2 = min(n, 1 << 20)
     b, kk = g2b[:n2].contiguous(), ks[:n2].contiguous()
     wout = torch.empty_like(b)
     ms = timeit(lambda: eng.g2_wnaf_mul(b, kk, 0, wout))
