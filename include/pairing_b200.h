@@ -95,6 +95,14 @@ int bls_g2_wnaf_mul_batch(bls_ctx*, const bls_g2* bases, const bls_fr_repr* k, b
 /* same with an explicit window 2..7 (the crate-internal wnaf_table/wnaf_form/wnaf_exp triple) */
 int bls_g1_wnaf_mul_window_batch(bls_ctx*, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n, int window);
 int bls_g2_wnaf_mul_window_batch(bls_ctx*, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n, int window);
+/* Fixed-base mode Wnaf::new().base(g, num_scalars) then .scalar(k_i) for every scalar (wnaf.rs:93-107,
+ * 169-178): ONE window table of 2^(window-1) entries (wnaf_table, wnaf.rs:4-15) shared by all scalars;
+ * `window` = recommended_wnaf_for_num_scalars(n) (ec.rs:907-921 / 1598-1612), 2..16.
+ * bls_g*_wnaf_table returns the table itself (2^(window-1) Jacobian points, bit-identical to the crate's). */
+int bls_g1_wnaf_fixed_base_batch(bls_ctx*, const bls_g1* base, int window, const bls_fr_repr* k, bls_g1* out, size_t n);
+int bls_g2_wnaf_fixed_base_batch(bls_ctx*, const bls_g2* base, int window, const bls_fr_repr* k, bls_g2* out, size_t n);
+int bls_g1_wnaf_table(bls_ctx*, const bls_g1* base, int window, bls_g1* table);
+int bls_g2_wnaf_table(bls_ctx*, const bls_g2* base, int window, bls_g2* table);
 /* CurveProjective::mul_assign (double-and-add), ec.rs:534-553 */
 int bls_g1_mul_batch(bls_ctx*, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n);
 int bls_g2_mul_batch(bls_ctx*, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n);
@@ -141,6 +149,11 @@ size_t bls_fq12_product_scratch_bytes(const bls_ctx*, size_t n);
 int bls_fq12_product_dev(bls_ctx*, const bls_fq12* in, size_t n, bls_fq12* out1, void* scratch, void* stream);
 int bls_g1_wnaf_mul_dev(bls_ctx*, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n, int window, void* stream);
 int bls_g2_wnaf_mul_dev(bls_ctx*, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n, int window, void* stream);
+/* fixed-base mode on the device: `table` holds 2^(window-1) points, built by bls_g*_wnaf_table_dev */
+int bls_g1_wnaf_table_dev(bls_ctx*, const bls_g1* base, int window, bls_g1* table, void* stream);
+int bls_g2_wnaf_table_dev(bls_ctx*, const bls_g2* base, int window, bls_g2* table, void* stream);
+int bls_g1_wnaf_fixed_base_dev(bls_ctx*, const bls_g1* table, int window, const bls_fr_repr* k, bls_g1* out, size_t n, void* stream);
+int bls_g2_wnaf_fixed_base_dev(bls_ctx*, const bls_g2* table, int window, const bls_fr_repr* k, bls_g2* out, size_t n, void* stream);
 /* scratch: bls_batch_normalization_scratch_bytes(ctx, degree, n) bytes; degree 1 = G1, 2 = G2 */
 size_t bls_batch_normalization_scratch_bytes(const bls_ctx*, int degree, size_t n);
 int bls_g1_batch_normalization_dev(bls_ctx*, bls_g1* inout, size_t n, void* scratch, void* stream);

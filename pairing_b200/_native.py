@@ -36,6 +36,8 @@ SYMBOLS = [
     "bls_multi_miller_loop_dev", "bls_fq12_product_scratch_bytes", "bls_fq12_product_dev",
     "bls_g1_wnaf_mul_dev", "bls_g2_wnaf_mul_dev", "bls_batch_normalization_scratch_bytes",
     "bls_g1_batch_normalization_dev", "bls_g2_batch_normalization_dev", "bls_imad_peak",
+    "bls_g1_wnaf_fixed_base_batch", "bls_g2_wnaf_fixed_base_batch", "bls_g1_wnaf_table", "bls_g2_wnaf_table",
+    "bls_g1_wnaf_table_dev", "bls_g2_wnaf_table_dev", "bls_g1_wnaf_fixed_base_dev", "bls_g2_wnaf_fixed_base_dev",
 ]
 
 
@@ -95,6 +97,14 @@ def load():
         "bls_g1_op_batch": [vp, ci, vp, vp, vp, sz],
         "bls_g2_op_batch": [vp, ci, vp, vp, vp, sz],
         "bls_field_op_batch": [vp, ci, ci, vp, vp, vp, vp, sz],
+        "bls_g1_wnaf_fixed_base_batch": [vp, vp, ci, vp, vp, sz],
+        "bls_g2_wnaf_fixed_base_batch": [vp, vp, ci, vp, vp, sz],
+        "bls_g1_wnaf_table": [vp, vp, ci, vp],
+        "bls_g2_wnaf_table": [vp, vp, ci, vp],
+        "bls_g1_wnaf_table_dev": [vp, vp, ci, vp, vp],
+        "bls_g2_wnaf_table_dev": [vp, vp, ci, vp, vp],
+        "bls_g1_wnaf_fixed_base_dev": [vp, vp, ci, vp, vp, sz, vp],
+        "bls_g2_wnaf_fixed_base_dev": [vp, vp, ci, vp, vp, sz, vp],
         "bls_g2_prepare_dev": [vp, vp, vp, sz, vp],
         "bls_miller_loop_dev": [vp, vp, vp, vp, sz, vp],
         "bls_miller_loop_prepared_dev": [vp, vp, vp, vp, sz, vp],
@@ -239,6 +249,33 @@ class Context:
             fn = L.bls_g2_wnaf_mul_batch if g2 else L.bls_g1_wnaf_mul_batch
             self._check(fn(self._ctx, _p(bases), _p(k), _p(out), n))
         return out
+
+    def _wnaf_fixed(self, g2, base, window, k):
+        """Wnaf::base(g, n).scalar(k_i): one shared table (window 2..16), every scalar against it."""
+        w = W_G2 if g2 else W_G1
+        base, k = _arr(base, w, "base"), _arr(k, W_FR, "k")
+        if base.shape[0] != 1:
+            raise ValueError("fixed-base mode takes exactly one base point")
+        out = np.zeros((k.shape[0], w), dtype=np.uint64)
+        fn = self._lib.bls_g2_wnaf_fixed_base_batch if g2 else self._lib.bls_g1_wnaf_fixed_base_batch
+        self._check(fn(self._ctx, _p(base), int(window), _p(k), _p(out), k.shape[0]))
+        return out
+
+    def g1_wnaf_fixed_base(self, base, window, k): return self._wnaf_fixed(False, base, window, k)
+    def g2_wnaf_fixed_base(self, base, window, k): return self._wnaf_fixed(True, base, window, k)
+
+    def _wnaf_table(self, g2, base, window):
+        w = W_G2 if g2 else W_G1
+        base = _arr(base, w, "base")
+        if not 2 <= int(window) <= 16:
+            raise ValueError("window must be in 2..16")
+        table = np.zeros((1 << (int(window) - 1), w), dtype=np.uint64)
+        fn = self._lib.bls_g2_wnaf_table if g2 else self._lib.bls_g1_wnaf_table
+        self._check(fn(self._ctx, _p(base), int(window), _p(table)))
+        return table
+
+    def g1_wnaf_table(self, base, window): return self._wnaf_table(False, base, window)
+    def g2_wnaf_table(self, base, window): return self._wnaf_table(True, base, window)
 
     def g1_wnaf_mul(self, bases, k, window=0): return self._wnaf(False, bases, k, window, "wnaf")
     def g2_wnaf_mul(self, bases, k, window=0): return self._wnaf(True, bases, k, window, "wnaf")

@@ -138,11 +138,12 @@ __device__ __forceinline__ int scalar_num_bits(const Scalar& k) {   // fr.rs:213
 __device__ __forceinline__ int g1_window_for_bits(int nb) { return nb >= 130 ? 4 : (nb >= 34 ? 3 : 2); }
 __device__ __forceinline__ int g2_window_for_bits(int nb) { return nb >= 103 ? 4 : (nb >= 37 ? 3 : 2); }
 
-#define BLS_MAX_WNAF_WINDOW 7
+#define BLS_MAX_WNAF_WINDOW 7          /* per-point tables */
+#define BLS_MAX_WNAF_FIXED_WINDOW 16   /* shared table: ec.rs:907-921 picks up to 16 (G1) / 15 (G2) */
 #define BLS_MAX_WNAF_TABLE (1 << (BLS_MAX_WNAF_WINDOW - 1))
 
-// wnaf_form, wnaf.rs:18-43.  Digits are odd in (-2^w, 2^w); |digit| < 128 for w <= 7.
-__device__ __forceinline__ int wnaf_form(int8_t* digits, Scalar c, int window) {
+// wnaf_form, wnaf.rs:18-43.  Digits are odd in (-2^w, 2^w): int8_t holds them for w <= 7, int32_t for w <= 16.
+template <class D> __device__ __forceinline__ int wnaf_form(D* digits, Scalar c, int window) {
   int n = 0;
   const uint32_t mask = (2u << window) - 1u;
   while (true) {
@@ -165,7 +166,7 @@ __device__ __forceinline__ int wnaf_form(int8_t* digits, Scalar c, int window) {
         c.v[i] = (uint32_t)t;
       }
     }
-    digits[n++] = (int8_t)u;
+    digits[n++] = (D)u;
 #pragma unroll
     for (int i = 0; i < 7; i++) c.v[i] = (c.v[i] >> 1) | (c.v[i + 1] << 31);
     c.v[7] >>= 1;
@@ -223,7 +224,9 @@ template <int K> struct WnafState {
   bool found[K];       // a non-zero digit has been consumed (wnaf.rs:52, found_one)
   bool doubled[K];     // the double of position i[j] has been done
 };
-template <class F, int K> __device__ __forceinline__ void pt_wnaf_run_lazy(Jac<F> (&res)[K], Jac<F> (&table)[K][8], int8_t (&digits)[K][260], WnafState<K>& st) {
+// `Tab::get(j, e)` returns entry e of the table of point j (per-point tables in local memory, or ONE shared
+// table in global memory for the fixed-base mode Wnaf::base(g, n).scalar(s), wnaf.rs:93-107, 169-178).
+template <class F, int K, class Tab, class D> __device__ __forceinline__ void pt_wnaf_run_lazy(Jac<F> (&res)[K], const Tab& table, D (&digits)[K][260], WnafState<K>& st) {
 #pragma unroll 1
   while (true) {
     // next group operation of every point of this lane: 0 = finished, 1 = double, 2 = add/sub of digit i
@@ -252,7 +255,7 @@ template <class F, int K> __device__ __forceinline__ void pt_wnaf_run_lazy(Jac<F
     if (pick >= 0) {
       if (do_add) {
         const int n = dig[pick];
-        Jac<F> t = table[pick][(n < 0 ? -n : n) >> 1];
+        Jac<F> t = table.get(pick, (n < 0 ? -n : n) >> 1);
         if (n < 0) pt_negate(t);             // sub_assign: copy, negate, add (lib.rs:156-160)
         pt_add(res[pick], t);
         st.found[pick] = true; st.doubled[pick] = false; st.i[pick]--;

@@ -477,6 +477,15 @@ __global__ void __launch_bounds__(128) k_wnaf_mul(const uint64_t* bases, const u
 #ifndef BLS_WNAF_MINB
 #define BLS_WNAF_MINB 3
 #endif
+template <class F, int K> struct LocalTables {
+  Jac<F> t[K][8];
+  __device__ __forceinline__ Jac<F> get(int j, int e) const { return t[j][e]; }
+};
+template <class F> struct SharedTable {
+  const uint64_t* p;   // 2^(w-1) Jacobian points in the ABI layout
+  __device__ __forceinline__ Jac<F> get(int, int e) const { Jac<F> r; ld_jac(r, p + (size_t)(3 * FW<F>::W) * e); return r; }
+};
+
 // K points per thread (pt_wnaf_run_lazy): thread t owns points t, t + T, ..., t + (K-1) T
 #ifndef BLS_WNAF_K
 #define BLS_WNAF_K 2
@@ -491,7 +500,7 @@ __global__ void __launch_bounds__(128, IS_G2 ? BLS_WNAF_MINB : BLS_WNAF_MINB + 1
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int PW = 3 * FW<F>::W;
   Jac<F> res[K];
-  Jac<F> table[K][8];
+  LocalTables<F, K> table;
   int8_t digits[K][260];
   WnafState<K> st;
 #pragma unroll 1
@@ -516,13 +525,62 @@ __global__ void __launch_bounds__(128, IS_G2 ? BLS_WNAF_MINB : BLS_WNAF_MINB + 1
     pt_double(dbl);
 #pragma unroll 1
     for (int e = 0; e < 8; e++) {          // wnaf_table, wnaf.rs:4-15 (the last add is unused)
-      if (e < tsize) { table[j][e] = b; if (e + 1 < tsize) pt_add(b, dbl); }
+      if (e < tsize) { table.t[j][e] = b; if (e + 1 < tsize) pt_add(b, dbl); }
     }
     st.i[j] = wnaf_form(digits[j], s, w) - 1;
     st.found[j] = false; st.doubled[j] = false;
     pt_set_zero(res[j]);
   }
   pt_wnaf_run_lazy<F, K>(res, table, digits, st);
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    size_t i = t + (size_t)j * T;
+    if (i < n) st_jac(out + (size_t)PW * i, res[j]);
+  }
+}
+
+// Fixed-base mode, Wnaf::new().base(g, num_scalars) then .scalar(s_i) per scalar (wnaf.rs:93-107, 169-178):
+// ONE window table shared by all scalars, window 2..16 from recommended_wnaf_for_num_scalars.
+// k_wnaf_table builds it: table[i] = (2i+1) g by repeated projective additions of 2g -- a chain of 2^(w-1)
+// dependent additions (each entry's Jacobian representative depends on the previous one), so one thread.
+template <class F>
+__global__ void __launch_bounds__(32) k_wnaf_table(const uint64_t* base, uint64_t* table, int window) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int PW = 3 * FW<F>::W;
+  Jac<F> b, dbl;
+  ld_jac(b, base);
+  dbl = b;
+  pt_double(dbl);
+  const int tsize = 1 << (window - 1);
+#pragma unroll 1
+  for (int e = 0; e < tsize; e++) {
+    st_jac(table + (size_t)PW * e, b);
+    if (e + 1 < tsize) pt_add(b, dbl);
+  }
+}
+template <class F, int K>
+__global__ void __launch_bounds__(128, BLS_WNAF_MINB) k_wnaf_fixed_base(const uint64_t* table, int window, const uint64_t* k, uint64_t* out, size_t n) {
+  const size_t T = (size_t)gridDim.x * blockDim.x;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int PW = 3 * FW<F>::W;
+  Jac<F> res[K];
+  SharedTable<F> tab{table};
+  int32_t digits[K][260];
+  WnafState<K> st;
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    size_t i = t + (size_t)j * T;
+    const bool active = i < n;
+    Scalar s = ld_scalar(k + 4 * (active ? i : n - 1));
+    if (!active) {
+#pragma unroll
+      for (int w = 0; w < 8; w++) s.v[w] = 0;
+    }
+    st.i[j] = wnaf_form(digits[j], s, window) - 1;
+    st.found[j] = false; st.doubled[j] = false;
+    pt_set_zero(res[j]);
+  }
+  pt_wnaf_run_lazy<F, K>(res, tab, digits, st);
 #pragma unroll 1
   for (int j = 0; j < K; j++) {
     size_t i = t + (size_t)j * T;
@@ -914,6 +972,37 @@ int bls_g2_wnaf_mul_dev(bls_ctx* ctx, const bls_g2* bases, const bls_fr_repr* k,
   return BLS_OK;
 }
 
+int bls_g1_wnaf_table_dev(bls_ctx* ctx, const bls_g1* base, int window, bls_g1* table, void* stream) {
+  if (!ctx || !base || !table || window < 2 || window > BLS_MAX_WNAF_FIXED_WINDOW) return BLS_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  k_wnaf_table<Fp><<<1, 32, 0, pick(ctx, stream)>>>((const uint64_t*)base, (uint64_t*)table, window);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_g2_wnaf_table_dev(bls_ctx* ctx, const bls_g2* base, int window, bls_g2* table, void* stream) {
+  if (!ctx || !base || !table || window < 2 || window > BLS_MAX_WNAF_FIXED_WINDOW) return BLS_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  k_wnaf_table<Fp2><<<1, 32, 0, pick(ctx, stream)>>>((const uint64_t*)base, (uint64_t*)table, window);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_g1_wnaf_fixed_base_dev(bls_ctx* ctx, const bls_g1* table, int window, const bls_fr_repr* k, bls_g1* out, size_t n, void* stream) {
+  if (!ctx || window < 2 || window > BLS_MAX_WNAF_FIXED_WINDOW || (n && (!table || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_wnaf_fixed_base<Fp, 2><<<blocks_for((n + 1) / 2, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)table, window, (const uint64_t*)k, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_g2_wnaf_fixed_base_dev(bls_ctx* ctx, const bls_g2* table, int window, const bls_fr_repr* k, bls_g2* out, size_t n, void* stream) {
+  if (!ctx || window < 2 || window > BLS_MAX_WNAF_FIXED_WINDOW || (n && (!table || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_wnaf_fixed_base<Fp2, 2><<<blocks_for((n + 1) / 2, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)table, window, (const uint64_t*)k, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+
 // threads for batch normalisation: >= 64 points per thread when n allows it
 static size_t bn_threads(const bls_ctx* ctx, size_t n) {
   size_t t = (n + 63) / 64;
@@ -1104,6 +1193,34 @@ int bls_g2_wnaf_mul_window_batch(bls_ctx* ctx, const bls_g2* b, const bls_fr_rep
 }
 int bls_g1_mul_batch(bls_ctx* ctx, const bls_g1* b, const bls_fr_repr* k, bls_g1* out, size_t n) { return wnaf_host(ctx, 1, b, k, out, n, 0, 1); }
 int bls_g2_mul_batch(bls_ctx* ctx, const bls_g2* b, const bls_fr_repr* k, bls_g2* out, size_t n) { return wnaf_host(ctx, 2, b, k, out, n, 0, 1); }
+
+// Wnaf::new().base(g, num_scalars).scalar(k_i): table built on the device, then every scalar against it
+static int wnaf_fixed_host(bls_ctx* ctx, int degree, const void* base, int window, const bls_fr_repr* k, void* out, size_t n, void* table_out) {
+  if (!ctx || !base || window < 2 || window > BLS_MAX_WNAF_FIXED_WINDOW || (n && (!k || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
+  size_t tsize = (size_t)1 << (window - 1);
+  H2D(db, base, pb);
+  DALLOC(dt, tsize * pb);
+  if (degree == 2) TRY(bls_g2_wnaf_table_dev(ctx, (const bls_g2*)db.p, window, (bls_g2*)dt.p, nullptr));
+  else TRY(bls_g1_wnaf_table_dev(ctx, (const bls_g1*)db.p, window, (bls_g1*)dt.p, nullptr));
+  if (table_out) D2H(table_out, dt, tsize * pb);
+  if (n) {
+    H2D(dk, k, n * sizeof(*k));
+    DALLOC(dout, n * pb);
+    if (degree == 2) TRY(bls_g2_wnaf_fixed_base_dev(ctx, (const bls_g2*)dt.p, window, (const bls_fr_repr*)dk.p, (bls_g2*)dout.p, n, nullptr));
+    else TRY(bls_g1_wnaf_fixed_base_dev(ctx, (const bls_g1*)dt.p, window, (const bls_fr_repr*)dk.p, (bls_g1*)dout.p, n, nullptr));
+    D2H(out, dout, n * pb);
+    SYNC();
+    return BLS_OK;
+  }
+  SYNC();
+  return BLS_OK;
+}
+int bls_g1_wnaf_fixed_base_batch(bls_ctx* ctx, const bls_g1* base, int window, const bls_fr_repr* k, bls_g1* out, size_t n) { return wnaf_fixed_host(ctx, 1, base, window, k, out, n, nullptr); }
+int bls_g2_wnaf_fixed_base_batch(bls_ctx* ctx, const bls_g2* base, int window, const bls_fr_repr* k, bls_g2* out, size_t n) { return wnaf_fixed_host(ctx, 2, base, window, k, out, n, nullptr); }
+int bls_g1_wnaf_table(bls_ctx* ctx, const bls_g1* base, int window, bls_g1* table) { return wnaf_fixed_host(ctx, 1, base, window, nullptr, nullptr, 0, table); }
+int bls_g2_wnaf_table(bls_ctx* ctx, const bls_g2* base, int window, bls_g2* table) { return wnaf_fixed_host(ctx, 2, base, window, nullptr, nullptr, 0, table); }
 
 static int bn_host(bls_ctx* ctx, int degree, void* inout, size_t n) {
   if (!ctx || (n && !inout)) return BLS_ERR_INVALID_ARGUMENT;

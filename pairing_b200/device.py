@@ -112,6 +112,25 @@ class DeviceEngine:
         self.ctx.call_dev("bls_g2_wnaf_mul_dev", bases.data_ptr(), k.data_ptr(), out.data_ptr(), bases.shape[0], window, self._stream())
         return out
 
+    def wnaf_table(self, base, window, g2=False):
+        """Wnaf::base(g, n): the shared window table (2^(window-1), W) on the device."""
+        w = nat.W_G2 if g2 else nat.W_G1
+        _check(base, w, "base")
+        table = torch.empty((1 << (window - 1), w), dtype=torch.int64, device=self.device)
+        self.ctx.call_dev("bls_g2_wnaf_table_dev" if g2 else "bls_g1_wnaf_table_dev", base.data_ptr(), window, table.data_ptr(), self._stream())
+        return table
+
+    def wnaf_fixed_base(self, table, window, k, g2=False, out=None):
+        """`.scalar(k_i)` for every scalar against one shared table."""
+        w = nat.W_G2 if g2 else nat.W_G1
+        _check(table, w, "table"); _check(k, nat.W_FR, "k")
+        if table.shape[0] != 1 << (window - 1):
+            raise ValueError("table has %d entries, window %d needs %d" % (table.shape[0], window, 1 << (window - 1)))
+        if out is None:
+            out = torch.empty((k.shape[0], w), dtype=torch.int64, device=self.device)
+        self.ctx.call_dev("bls_g2_wnaf_fixed_base_dev" if g2 else "bls_g1_wnaf_fixed_base_dev", table.data_ptr(), window, k.data_ptr(), out.data_ptr(), k.shape[0], self._stream())
+        return out
+
     def g1_batch_normalization_(self, v):
         _check(v, nat.W_G1, "v")
         scr = self._buf("bn", self.ctx.batch_normalization_scratch_bytes(1, v.shape[0]))

@@ -223,8 +223,9 @@ class Wnaf:
     """The reference's typestate builder (wnaf.rs:75-179), batch-shaped.
 
     Wnaf().scalar(k).base(g)   per-(base, scalar) mode: window from each scalar's bit length
-    Wnaf().base(g, n)          fixed-base mode: window from the number of scalars -- only windows
-                               <= 7 run on the GPU in this round (SURVEY.md 8f item 1 is "next")
+    Wnaf().base(g, n)          fixed-base mode: window from the number of scalars (4..16 for G1, 4..15 for
+                               G2, ec.rs:907-921 / 1598-1612); ONE table is built on the device and shared
+                               by every `.scalar(s)` (wnaf.rs:93-107, 169-178)
     """
 
     def __init__(self, curve=G1, ctx=None):
@@ -237,9 +238,10 @@ class Wnaf:
     def scalar(self, scalars):
         w = Wnaf(self._curve, self._ctx)
         w._scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
-        if self._base is not None:                      # `.base(g, n).scalar(s)`: exponentiate now
-            b = np.repeat(self._base, w._scalars.shape[0], 0) if self._base.shape[0] == 1 else self._base
-            return self._run(b, w._scalars, self._window)
+        if self._base is not None:                      # `.base(g, n).scalar(s)`: exponentiate now, shared table
+            c = _ctx(self._ctx)
+            fn = c.g2_wnaf_fixed_base if self._curve._g2 else c.g1_wnaf_fixed_base
+            return fn(self._base, self._window, w._scalars.reshape(-1, 4))
         return w
 
     def base(self, base, num_scalars=None):
@@ -250,9 +252,11 @@ class Wnaf:
             return self._run(base, self._scalars, 0)
         w = Wnaf(self._curve, self._ctx)
         w._base = base
+        if base.ndim == 1:
+            base = base.reshape(1, -1)
+        if base.shape[0] != 1:
+            raise ValueError("Wnaf.base(g, n) takes one base point")
         w._window = self._curve.recommended_wnaf_for_num_scalars(num_scalars)
-        if w._window > 7:
-            raise nat.BlsError("fixed-base windows above 7 are not on the GPU path yet (window %d)" % w._window)
         return w
 
     def shared(self):

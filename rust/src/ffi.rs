@@ -36,6 +36,10 @@ extern "C" {
     pub fn bls_g2_wnaf_mul_batch(ctx: *mut bls_ctx, bases: *const bls_g2, k: *const bls_fr_repr, out: *mut bls_g2, n: usize) -> c_int;
     pub fn bls_g1_wnaf_mul_window_batch(ctx: *mut bls_ctx, bases: *const bls_g1, k: *const bls_fr_repr, out: *mut bls_g1, n: usize, window: c_int) -> c_int;
     pub fn bls_g2_wnaf_mul_window_batch(ctx: *mut bls_ctx, bases: *const bls_g2, k: *const bls_fr_repr, out: *mut bls_g2, n: usize, window: c_int) -> c_int;
+    pub fn bls_g1_wnaf_fixed_base_batch(ctx: *mut bls_ctx, base: *const bls_g1, window: c_int, k: *const bls_fr_repr, out: *mut bls_g1, n: usize) -> c_int;
+    pub fn bls_g2_wnaf_fixed_base_batch(ctx: *mut bls_ctx, base: *const bls_g2, window: c_int, k: *const bls_fr_repr, out: *mut bls_g2, n: usize) -> c_int;
+    pub fn bls_g1_wnaf_table(ctx: *mut bls_ctx, base: *const bls_g1, window: c_int, table: *mut bls_g1) -> c_int;
+    pub fn bls_g2_wnaf_table(ctx: *mut bls_ctx, base: *const bls_g2, window: c_int, table: *mut bls_g2) -> c_int;
     pub fn bls_g1_mul_batch(ctx: *mut bls_ctx, bases: *const bls_g1, k: *const bls_fr_repr, out: *mut bls_g1, n: usize) -> c_int;
     pub fn bls_g2_mul_batch(ctx: *mut bls_ctx, bases: *const bls_g2, k: *const bls_fr_repr, out: *mut bls_g2, n: usize) -> c_int;
     pub fn bls_g1_batch_normalization(ctx: *mut bls_ctx, inout: *mut bls_g1, n: usize) -> c_int;

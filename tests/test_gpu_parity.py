@@ -215,3 +215,41 @@ def test_imad_peak_runs(ctx):
     for variant in (0, 1, 2):
         macs, ms = ctx.imad_peak(variant, 200)
         assert macs > 1e11 and ms > 0
+
+
+@pytest.mark.parametrize("g2", [False, True])
+@pytest.mark.parametrize("w", [2, 4, 7, 8, 11])
+def test_wnaf_fixed_base(ctx, g2, w):
+    """Wnaf::base(g, n).scalar(s) (wnaf.rs:93-107, 169-178): one shared table; per scalar the result is the
+    reference's wnaf_exp(wnaf_table(g, w), wnaf_form(s, w)) -- the oracle's explicit-window path on the same base."""
+    n = 70
+    base = (dg.g2_points if g2 else dg.g1_points)(1, 60 + w)
+    k = dg.rand_scalars(n, 61 + w)
+    want = (o.g2_op if g2 else o.g1_op)("wnaf", np.repeat(base, n, 0), k=k, window=w, threads=TH)
+    got = (ctx.g2_wnaf_fixed_base if g2 else ctx.g1_wnaf_fixed_base)(base, w, k)
+    eq(got, want)
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_wnaf_table_and_builder(ctx, g2):
+    """wnaf_table (wnaf.rs:4-15): table[i] = (2i+1) g as the chain of projective additions of 2g; and the
+    typestate builder picks the window from the number of scalars (ec.rs:907-921 / 1598-1612)."""
+    from pairing_b200 import engine
+    curve = engine.G2 if g2 else engine.G1
+    op_o = o.g2_op if g2 else o.g1_op
+    base = (dg.g2_points if g2 else dg.g1_points)(1, 77)
+    table = (ctx.g2_wnaf_table if g2 else ctx.g1_wnaf_table)(base, 6)
+    want = [base]
+    dbl = op_o("double", base)
+    for _ in range(31):
+        want.append(op_o("add", want[-1], dbl))
+    eq(table, np.concatenate(want))
+    for num_scalars in (1, 50, 2000):                       # windows 4, 9, 13 (G1) / 4, 9, 12 (G2)
+        w = curve.recommended_wnaf_for_num_scalars(num_scalars)
+        k = dg.rand_scalars(12, 78 + num_scalars)
+        got = engine.Wnaf(curve, ctx).base(base, num_scalars).scalar(k)
+        eq(got, op_o("wnaf", np.repeat(base, 12, 0), k=k, window=w, threads=TH))
+    inf = base.copy(); inf[:] = 0
+    inf[0, (12 if g2 else 6):(18 if g2 else 12)] = np.array(m.limbs64(m.MONT_R), dtype=np.uint64)
+    k = dg.rand_scalars(5, 90)
+    eq((ctx.g2_wnaf_fixed_base if g2 else ctx.g1_wnaf_fixed_base)(inf, 5, k), op_o("wnaf", np.repeat(inf, 5, 0), k=k, window=5, threads=TH))
