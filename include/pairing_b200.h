@@ -85,6 +85,10 @@ int bls_pairing_batch(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, 
  * products before the single final exponentiation of a sharded multi_miller_loop. */
 int bls_fq12_product(bls_ctx*, const bls_fq12* in, size_t n, bls_fq12* out1);
 
+/* Field::pow on Fq12 with an FrRepr exponent (lib.rs:306-324): GT exponentiation e(P,Q)^k, the step after
+ * the path in the reference's bilinearity test (tests/engine.rs:93-126). */
+int bls_fq12_pow_batch(bls_ctx*, const bls_fq12* a, const bls_fr_repr* k, bls_fq12* out, size_t n);
+
 /* ------------------------------------------------------------------ curve groups (host buffers) */
 
 /* Wnaf::new().scalar(k_i).base(g_i): window from the scalar (ec.rs:895-905 / 1586-1596),
@@ -142,6 +146,7 @@ int bls_miller_loop_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q
 int bls_miller_loop_prepared_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q, bls_fq12* out, size_t n, void* stream);
 int bls_final_exponentiation_dev(bls_ctx*, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n, void* stream);
 int bls_pairing_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream);
+int bls_fq12_pow_dev(bls_ctx*, const bls_fq12* a, const bls_fr_repr* k, bls_fq12* out, size_t n, void* stream);
 /* scratch: bls_multi_miller_scratch_bytes(ctx, n) bytes */
 size_t bls_multi_miller_scratch_bytes(const bls_ctx*, size_t n);
 int bls_multi_miller_loop_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, void* scratch, void* stream);

@@ -37,6 +37,7 @@ SYMBOLS = [
     "bls_g1_wnaf_mul_dev", "bls_g2_wnaf_mul_dev", "bls_batch_normalization_scratch_bytes",
     "bls_g1_batch_normalization_dev", "bls_g2_batch_normalization_dev", "bls_imad_peak",
     "bls_g1_wnaf_fixed_base_batch", "bls_g2_wnaf_fixed_base_batch", "bls_g1_wnaf_table", "bls_g2_wnaf_table",
+    "bls_fq12_pow_batch", "bls_fq12_pow_dev",
     "bls_g1_wnaf_table_dev", "bls_g2_wnaf_table_dev", "bls_g1_wnaf_fixed_base_dev", "bls_g2_wnaf_fixed_base_dev",
 ]
 
@@ -105,6 +106,8 @@ def load():
         "bls_g2_wnaf_table_dev": [vp, vp, ci, vp, vp],
         "bls_g1_wnaf_fixed_base_dev": [vp, vp, ci, vp, vp, sz, vp],
         "bls_g2_wnaf_fixed_base_dev": [vp, vp, ci, vp, vp, sz, vp],
+        "bls_fq12_pow_batch": [vp, vp, vp, vp, sz],
+        "bls_fq12_pow_dev": [vp, vp, vp, vp, sz, vp],
         "bls_g2_prepare_dev": [vp, vp, vp, sz, vp],
         "bls_miller_loop_dev": [vp, vp, vp, vp, sz, vp],
         "bls_miller_loop_prepared_dev": [vp, vp, vp, vp, sz, vp],
@@ -223,6 +226,15 @@ class Context:
         ok = np.zeros(f.shape[0], dtype=np.uint8)
         self._check(self._lib.bls_final_exponentiation_batch(self._ctx, _p(f), _p(out), _p(ok), f.shape[0]))
         return out, ok
+
+    def fq12_pow(self, a, k):
+        """Fq12::pow(FrRepr) per element (lib.rs:306-324)."""
+        a, k = _arr(a, W_FQ12, "a"), _arr(k, W_FR, "k")
+        if a.shape[0] != k.shape[0]:
+            raise ValueError("a and k must have the same length")
+        out = np.zeros_like(a)
+        self._check(self._lib.bls_fq12_pow_batch(self._ctx, _p(a), _p(k), _p(out), a.shape[0]))
+        return out
 
     def fq12_product(self, f):
         f = _arr(f, W_FQ12, "f")

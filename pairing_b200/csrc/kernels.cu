@@ -294,6 +294,36 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_final_exp(
   }
 }
 
+// Field::pow on Fq12 with an FrRepr exponent (lib.rs:306-324; GT exponentiation, tests/engine.rs:121):
+// MSB-first square-and-multiply.  The exponent differs per lane pair, so the loop is branch-free over all
+// 256 bits (every lane has to reach every shuffle): squarings and products are computed for the whole warp
+// and committed per lane pair.  Generic squaring (the input need not be in the cyclotomic subgroup).
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_fq12_pow(const uint64_t* in, const uint64_t* k, uint64_t* out, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = t >> 1;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  P12 a, res, tmp;
+  ld_p12(a, in + FQ12_W * i);
+  Scalar s = ld_scalar(k + 4 * i);
+  p12_one(res);
+  bool found = false;
+#pragma unroll 1
+  for (int b = 255; b >= 0; b--) {
+    const bool bit = (s.v[b >> 5] >> (b & 31)) & 1u;
+    if (__any_sync(0xffffffffu, found)) {
+      p12_sqr(tmp, res);
+      p12_select(res, found, tmp, res);
+    }
+    found |= bit;
+    if (__any_sync(0xffffffffu, bit)) {
+      p12_mul(tmp, res, a);
+      p12_select(res, bit, tmp, res);
+    }
+  }
+  if (active) st_p12(out + FQ12_W * i, res);
+}
+
 // Miller loop from stored coefficients, the reference's literal miller_loop (mod.rs:40-102), one pair
 __device__ __forceinline__ void miller_loop_prepared_single(Fp12& f, const Fp& px, const Fp& py, const uint64_t* coeffs, bool live) {
   fp12_one(f);
@@ -877,6 +907,15 @@ int bls_pairing_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q
   return BLS_OK;
 }
 
+int bls_fq12_pow_dev(bls_ctx* ctx, const bls_fq12* a, const bls_fr_repr* k, bls_fq12* out, size_t n, void* stream) {
+  if (!ctx || (n && (!a || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_pair_fq12_pow<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)a, (const uint64_t*)k, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+
 // threads (= partial products) of the thread-per-element multi-Miller kernel over prepared coefficients
 static size_t mm_threads_prepared(const bls_ctx* ctx, size_t n) {
   size_t full = (size_t)ctx->sm_count * 2 * TPB;
@@ -1157,6 +1196,19 @@ int bls_fq12_product(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq12* out1)
   DALLOC(dout, sizeof(*out1));
   TRY(bls_fq12_product_dev(ctx, (const bls_fq12*)din.p, n, (bls_fq12*)dout.p, dscr.p, nullptr));
   D2H(out1, dout, sizeof(*out1));
+  SYNC();
+  return BLS_OK;
+}
+
+int bls_fq12_pow_batch(bls_ctx* ctx, const bls_fq12* a, const bls_fr_repr* k, bls_fq12* out, size_t n) {
+  if (!ctx || (n && (!a || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  H2D(da, a, n * sizeof(*a));
+  H2D(dk, k, n * sizeof(*k));
+  DALLOC(dout, n * sizeof(*out));
+  TRY(bls_fq12_pow_dev(ctx, (const bls_fq12*)da.p, (const bls_fr_repr*)dk.p, (bls_fq12*)dout.p, n, nullptr));
+  D2H(out, dout, n * sizeof(*out));
   SYNC();
   return BLS_OK;
 }

@@ -161,6 +161,10 @@ __device__ __noinline__ void p6_frobenius(P6& r, const P6& a, int power) {
 // ------------------------------------------------------------------------------------------ Fq12
 __device__ __forceinline__ void p12_one(P12& r) { p6_zero(r.c0); p6_zero(r.c1); r.c0.c0 = p2_one(); }
 __device__ __forceinline__ void p12_conjugate(P12& a) { p6_neg(a.c1, a.c1); }   // fq12.rs:30-32
+__device__ __forceinline__ void p6_select(P6& r, bool take_a, const P6& a, const P6& b) {
+  r.c0.v = fp_select(take_a, a.c0.v, b.c0.v); r.c1.v = fp_select(take_a, a.c1.v, b.c1.v); r.c2.v = fp_select(take_a, a.c2.v, b.c2.v);
+}
+__device__ __forceinline__ void p12_select(P12& r, bool take_a, const P12& a, const P12& b) { p6_select(r.c0, take_a, a.c0, b.c0); p6_select(r.c1, take_a, a.c1, b.c1); }
 // fq12.rs:116-130 (r may alias a or b)
 __device__ __noinline__ void p12_mul(P12& r, const P12& a, const P12& b) {
   P6 aa, bb, o, s;

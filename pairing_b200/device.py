@@ -88,6 +88,13 @@ class DeviceEngine:
         self.ctx.call_dev("bls_multi_miller_loop_dev", p.data_ptr(), q.data_ptr(), n, out.data_ptr(), scr.data_ptr(), self._stream())
         return out
 
+    def fq12_pow(self, a, k, out=None):
+        _check(a, nat.W_FQ12, "a"); _check(k, nat.W_FR, "k")
+        if out is None:
+            out = torch.empty_like(a)
+        self.ctx.call_dev("bls_fq12_pow_dev", a.data_ptr(), k.data_ptr(), out.data_ptr(), a.shape[0], self._stream())
+        return out
+
     def fq12_product(self, f, out=None):
         _check(f, nat.W_FQ12, "f")
         n = f.shape[0]

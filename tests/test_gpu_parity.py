@@ -253,3 +253,35 @@ def test_wnaf_table_and_builder(ctx, g2):
     inf[0, (12 if g2 else 6):(18 if g2 else 12)] = np.array(m.limbs64(m.MONT_R), dtype=np.uint64)
     k = dg.rand_scalars(5, 90)
     eq((ctx.g2_wnaf_fixed_base if g2 else ctx.g1_wnaf_fixed_base)(inf, 5, k), op_o("wnaf", np.repeat(inf, 5, 0), k=k, window=5, threads=TH))
+
+
+def _oracle_fq12_pow(a, k):
+    """a_i^(k_i) for 256-bit k from the oracle's u64 pow: prod_j (a^(2^(64 j)))^(limb_j)"""
+    out = None
+    base = a.copy()
+    for j in range(4):
+        term = np.concatenate([o.fq12_pow_u64(base[i:i + 1], int(k[i, j])) for i in range(len(a))])
+        out = term if out is None else o.fq12_op("mul", out, term)[0]
+        if j < 3:
+            base = np.concatenate([o.fq12_pow_u64(o.fq12_pow_u64(base[i:i + 1], 1 << 63), 2) for i in range(len(a))])
+    return out
+
+
+def test_fq12_pow_and_bilinearity(ctx):
+    """Field::pow (lib.rs:306-324) on Fq12 and the reference's bilinearity check (tests/engine.rs:93-126):
+    e([a]P, [b]Q) == e(P, Q)^(ab) computed as (e(P,Q)^a)^b, == e([ab]P, Q)."""
+    n = 40
+    f = dg.rand_field(n, 12, 50)
+    k = dg.rand_scalars(n, 51)                     # includes 0, 1, r-1 and the window-threshold scalars
+    eq(ctx.fq12_pow(f, k), _oracle_fq12_pow(f, k))
+    p = dg.g1_points(n, 52); q = dg.g2_points(n, 53)
+    a = dg.rand_scalars(n, 54, edge_cases=False); b = dg.rand_scalars(n, 55, edge_cases=False)
+    pa, qa = ctx.g1_into_affine(p), ctx.g2_into_affine(q)
+    ap = ctx.g1_into_affine(ctx.g1_wnaf_mul(p, a)); bq = ctx.g2_into_affine(ctx.g2_wnaf_mul(q, b))
+    lhs = ctx.pairing(ap, bq)
+    rhs = ctx.fq12_pow(ctx.fq12_pow(ctx.pairing(pa, qa), a), b)
+    eq(lhs, rhs)
+    one = np.zeros((n, 72), dtype=np.uint64); one[:, :6] = np.array(m.limbs64(m.MONT_R), dtype=np.uint64)
+    assert not np.array_equal(lhs, one)
+    r = np.repeat(np.array([m.limbs64(m.R_ORDER, 4)], dtype=np.uint64), n, 0)     # GT has order r
+    eq(ctx.fq12_pow(lhs, r), one)
