@@ -122,6 +122,21 @@ enum { BLS_PT_DOUBLE = 0, BLS_PT_ADD = 1, BLS_PT_ADD_MIXED = 2, BLS_PT_NEGATE = 
 int bls_g1_op_batch(bls_ctx*, int op, const bls_g1* a, const void* b, bls_g1* out, size_t n);
 int bls_g2_op_batch(bls_ctx*, int op, const bls_g2* a, const void* b, bls_g2* out, size_t n);
 
+/* ------------------------------------------------------------------ point encodings (host buffers)
+ * EncodedPoint::into_affine (checked != 0: on-curve and r-order-subgroup checks) / into_affine_unchecked and
+ * EncodedPoint::from_affine for G1Uncompressed (96 B) / G1Compressed (48 B) (ec.rs:645-868) and
+ * G2Uncompressed (192 B) / G2Compressed (96 B) (ec.rs:1292-1540).  `bytes` holds n encodings back to back.
+ * status[i] mirrors GroupDecodingError (src/lib.rs:468-497); a rejected element decodes to the zero point. */
+enum {
+  BLS_DEC_OK = 0, BLS_DEC_UNEXPECTED_COMPRESSION_MODE = 1, BLS_DEC_UNEXPECTED_INFORMATION = 2,
+  BLS_DEC_NOT_ON_CURVE = 3, BLS_DEC_NOT_IN_SUBGROUP = 4,
+  BLS_DEC_COORDINATE = 16 /* + coordinate: G1 0 = x, 1 = y; G2 0 = x (c0), 1 = x (c1), 2 = y (c0), 3 = y (c1) */
+};
+int bls_g1_decode_batch(bls_ctx*, const uint8_t* bytes, int compressed, int checked, bls_g1_affine* out, uint8_t* status, size_t n);
+int bls_g2_decode_batch(bls_ctx*, const uint8_t* bytes, int compressed, int checked, bls_g2_affine* out, uint8_t* status, size_t n);
+int bls_g1_encode_batch(bls_ctx*, const bls_g1_affine* in, int compressed, uint8_t* bytes, size_t n);
+int bls_g2_encode_batch(bls_ctx*, const bls_g2_affine* in, int compressed, uint8_t* bytes, size_t n);
+
 /* ------------------------------------------------------------------ field tower (host buffers) */
 /* Element-wise field operations, the `Field` trait methods of src/lib.rs:267-325 on
  * Fq (degree 1), Fq2 (2), Fq6 (6), Fq12 (12).  `b` is an array of the same element type or NULL.

@@ -727,3 +727,158 @@ def to_bytes(x):
 def fq2_from_bytes(b): return (fq_from_bytes(b[:48]), fq_from_bytes(b[48:96]))
 def fq6_from_bytes(b): return tuple(fq2_from_bytes(b[96 * i:96 * i + 96]) for i in range(3))
 def fq12_from_bytes(b): return (fq6_from_bytes(b[:288]), fq6_from_bytes(b[288:576]))
+
+
+# ----------------------------------------------------------------------------------------------
+# Point encodings and their validation (the step BEFORE the path in batch
+# verification -- bytes -> affine points).  ec.rs:97-144 (get_point_from_x, is_on_curve, subgroup check),
+# ec.rs:645-868 (G1Uncompressed / G1Compressed), ec.rs:1292-1540 (G2), fq.rs:1147-1170 (Fq::sqrt),
+# fq2.rs:167-221 (Fq2::sqrt), fq.rs:703-708 + fq2.rs:20-31 (orderings).
+# Pinned by the reference's k*G vector files and its invalid-vector tests (bls12_381/tests/mod.rs:55-611).
+# ----------------------------------------------------------------------------------------------
+DEC_OK, DEC_UNEXPECTED_COMPRESSION_MODE, DEC_UNEXPECTED_INFORMATION, DEC_NOT_ON_CURVE, DEC_NOT_IN_SUBGROUP = 0, 1, 2, 3, 4
+DEC_COORDINATE = 16          # + index: G1 0 = "x coordinate", 1 = "y coordinate";
+#                              G2 0 = "x coordinate (c0)", 1 = "x coordinate (c1)", 2 = "y coordinate (c0)", 3 = "y coordinate (c1)"
+SQRT_EXP = (Q - 3) // 4      # fq.rs:1152-1159
+assert SQRT_EXP == from_limbs64([0xee7fbfffffffeaaa, 0x7aaffffac54ffff, 0xd9cc34a83dac3d89, 0xd91dd2e13ce144af, 0x92c6e9ed90d2eb35, 0x680447a8e5ff9a6])
+G1_B = 4                     # y^2 = x^3 + 4
+G2_B = (4, 4)                # y^2 = x^3 + 4(1 + u)
+
+
+def fq_sqrt(a):
+    """fq.rs:1147-1170 (Shanks for q = 3 mod 4): returns the specific root the reference returns, or None."""
+    a1 = pow(a, SQRT_EXP, Q)
+    a0 = a1 * a1 % Q * a % Q
+    if a0 == Q - 1:
+        return None
+    return a1 * a % Q
+
+
+def fq2_sqrt(a):
+    """fq2.rs:167-221 (Algorithm 9 of eprint 2012/685)."""
+    if fq2_is_zero(a):
+        return FQ2_ZERO
+    a1 = fq2_pow(a, SQRT_EXP)
+    alpha = fq2_mul(fq2_sqr(a1), a)
+    a0 = fq2_mul(fq2_frobenius(alpha, 1), alpha)
+    neg1 = (Q - 1, 0)
+    if a0 == neg1:
+        return None
+    a1 = fq2_mul(a1, a)
+    if alpha == neg1:
+        return fq2_mul(a1, (0, 1))
+    alpha = fq2_pow(fq2_add(alpha, FQ2_ONE), (Q - 1) // 2)
+    return fq2_mul(a1, alpha)
+
+
+def _fq2_key(a):             # Fq2 ordering: c1 first, then c0 (fq2.rs:20-31)
+    return (a[1], a[0])
+
+
+def get_point_from_x(x, greatest, g2):
+    """ec.rs:102-123"""
+    if g2:
+        y = fq2_sqrt(fq2_add(fq2_mul(fq2_sqr(x), x), G2_B))
+        if y is None:
+            return None
+        negy = fq2_neg(y)
+        return (x, y if (_fq2_key(y) < _fq2_key(negy)) ^ greatest else negy, False)
+    y = fq_sqrt((x * x % Q * x + G1_B) % Q)
+    if y is None:
+        return None
+    negy = fq_neg(y)
+    return (x, y if (y < negy) ^ greatest else negy, False)
+
+
+def is_on_curve(p, g2):
+    """ec.rs:125-140"""
+    x, y, inf = p
+    if inf:
+        return True
+    if g2:
+        return fq2_sqr(y) == fq2_add(fq2_mul(fq2_sqr(x), x), G2_B)
+    return y * y % Q == (x * x % Q * x + G1_B) % Q
+
+
+def is_in_correct_subgroup_assuming_on_curve(p, g2):
+    """ec.rs:142-144: self.mul(Fr::char()).is_zero()"""
+    F = _F2 if g2 else _F1
+    return pt_is_zero(F, pt_mul(F, pt_from_affine(F, p), R_ORDER))
+
+
+def _affine_zero(g2):
+    return (FQ2_ZERO, FQ2_ONE, True) if g2 else (0, 1, True)
+
+
+def decode_point(b, g2, compressed, checked=True):
+    """EncodedPoint::into_affine / into_affine_unchecked.  Returns (status, affine or None)."""
+    b = bytearray(b)
+    ncoord = (2 if g2 else 1) * (1 if compressed else 2)
+    assert len(b) == 48 * ncoord
+    if bool(b[0] & 0x80) != bool(compressed):
+        return DEC_UNEXPECTED_COMPRESSION_MODE, None
+    if b[0] & 0x40:
+        b[0] &= 0x3f
+        if any(b):
+            return DEC_UNEXPECTED_INFORMATION, None
+        return DEC_OK, _affine_zero(g2)
+    greatest = bool(b[0] & 0x20)
+    if greatest and not compressed:
+        return DEC_UNEXPECTED_INFORMATION, None
+    b[0] &= 0x1f
+    vals = [int.from_bytes(b[48 * i:48 * i + 48], "big") for i in range(ncoord)]
+    if g2:
+        # bytes hold c1 then c0; the reference converts c0 first, then c1 (ec.rs:1378-1393, 1480-1487)
+        order = [(1, 0), (0, 1)] + ([(3, 2), (2, 3)] if not compressed else [])     # (byte slot, coordinate index)
+        for slot, idx in order:
+            if vals[slot] >= Q:
+                return DEC_COORDINATE + idx, None
+        x = (vals[1], vals[0])
+        if compressed:
+            p = get_point_from_x(x, greatest, True)
+            if p is None:
+                return DEC_NOT_ON_CURVE, None
+        else:
+            p = (x, (vals[3], vals[2]), False)
+    else:
+        for idx, v in enumerate(vals):
+            if v >= Q:
+                return DEC_COORDINATE + idx, None
+        if compressed:
+            p = get_point_from_x(vals[0], greatest, False)
+            if p is None:
+                return DEC_NOT_ON_CURVE, None
+        else:
+            p = (vals[0], vals[1], False)
+    if checked:
+        if not compressed and not is_on_curve(p, g2):
+            return DEC_NOT_ON_CURVE, None
+        if not is_in_correct_subgroup_assuming_on_curve(p, g2):
+            return DEC_NOT_IN_SUBGROUP, None
+    return DEC_OK, p
+
+
+def encode_point(p, g2, compressed):
+    """EncodedPoint::from_affine (ec.rs:739-757, 846-867, 1397-1416, 1519-1540)."""
+    x, y, inf = p
+    ncoord = (2 if g2 else 1) * (1 if compressed else 2)
+    b = bytearray(48 * ncoord)
+    if inf:
+        b[0] |= 0x40
+    else:
+        e = lambda v: v.to_bytes(48, "big")
+        if g2:
+            b[:96] = e(x[1]) + e(x[0])
+            if not compressed:
+                b[96:] = e(y[1]) + e(y[0])
+            greatest = _fq2_key(y) > _fq2_key(fq2_neg(y))
+        else:
+            b[:48] = e(x)
+            if not compressed:
+                b[48:] = e(y)
+            greatest = y > fq_neg(y)
+        if compressed and greatest:
+            b[0] |= 0x20
+    if compressed:
+        b[0] |= 0x80
+    return bytes(b)

@@ -38,6 +38,7 @@ SYMBOLS = [
     "bls_g1_batch_normalization_dev", "bls_g2_batch_normalization_dev", "bls_imad_peak",
     "bls_g1_wnaf_fixed_base_batch", "bls_g2_wnaf_fixed_base_batch", "bls_g1_wnaf_table", "bls_g2_wnaf_table",
     "bls_fq12_pow_batch", "bls_fq12_pow_dev",
+    "bls_g1_decode_batch", "bls_g2_decode_batch", "bls_g1_encode_batch", "bls_g2_encode_batch",
     "bls_g1_wnaf_table_dev", "bls_g2_wnaf_table_dev", "bls_g1_wnaf_fixed_base_dev", "bls_g2_wnaf_fixed_base_dev",
 ]
 
@@ -106,6 +107,10 @@ def load():
         "bls_g2_wnaf_table_dev": [vp, vp, ci, vp, vp],
         "bls_g1_wnaf_fixed_base_dev": [vp, vp, ci, vp, vp, sz, vp],
         "bls_g2_wnaf_fixed_base_dev": [vp, vp, ci, vp, vp, sz, vp],
+        "bls_g1_decode_batch": [vp, vp, ci, ci, vp, vp, sz],
+        "bls_g2_decode_batch": [vp, vp, ci, ci, vp, vp, sz],
+        "bls_g1_encode_batch": [vp, vp, ci, vp, sz],
+        "bls_g2_encode_batch": [vp, vp, ci, vp, sz],
         "bls_fq12_pow_batch": [vp, vp, vp, vp, sz],
         "bls_fq12_pow_dev": [vp, vp, vp, vp, sz, vp],
         "bls_g2_prepare_dev": [vp, vp, vp, sz, vp],
@@ -261,6 +266,29 @@ class Context:
             fn = L.bls_g2_wnaf_mul_batch if g2 else L.bls_g1_wnaf_mul_batch
             self._check(fn(self._ctx, _p(bases), _p(k), _p(out), n))
         return out
+
+    def decode(self, g2, data, compressed, checked=True):
+        """EncodedPoint::into_affine(_unchecked) for n encodings back to back -> (affine rows, status bytes)."""
+        size = (96 if g2 else 48) * (1 if compressed else 2)
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        if buf.size % size:
+            raise ValueError("encoded data is not a multiple of %d bytes" % size)
+        n = buf.size // size
+        out = np.zeros((n, W_G2A if g2 else W_G1A), dtype=np.uint64)
+        status = np.zeros(n, dtype=np.uint8)
+        buf = np.ascontiguousarray(buf)
+        fn = self._lib.bls_g2_decode_batch if g2 else self._lib.bls_g1_decode_batch
+        self._check(fn(self._ctx, _p(buf), int(bool(compressed)), int(bool(checked)), _p(out), _p(status), n))
+        return out, status
+
+    def encode(self, g2, affine, compressed):
+        """EncodedPoint::from_affine for n affine points -> bytes."""
+        affine = _arr(affine, W_G2A if g2 else W_G1A, "affine")
+        size = (96 if g2 else 48) * (1 if compressed else 2)
+        out = np.zeros(affine.shape[0] * size, dtype=np.uint8)
+        fn = self._lib.bls_g2_encode_batch if g2 else self._lib.bls_g1_encode_batch
+        self._check(fn(self._ctx, _p(affine), int(bool(compressed)), _p(out), affine.shape[0]))
+        return out.tobytes()
 
     def _wnaf_fixed(self, g2, base, window, k):
         """Wnaf::base(g, n).scalar(k_i): one shared table (window 2..16), every scalar against it."""

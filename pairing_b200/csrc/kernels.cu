@@ -16,6 +16,7 @@
 #include "../../include/pairing_b200.h"
 #include "pairing.cuh"
 #include "pair_tower.cuh"
+#include "codec.cuh"
 
 using namespace bls;
 
@@ -704,6 +705,31 @@ __global__ void __launch_bounds__(128) k_batch_normalization(uint64_t* pts, size
 }
 
 // ------------------------------------------------------------------------------------------------
+// Point encodings (codec.cuh): thread per element
+// ------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) k_decode(const uint8_t* bytes, int compressed, int checked, uint64_t* out, uint8_t* status, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int AW = 2 * FW<F>::W + 1;
+  const size_t size = (size_t)FBytes<F>::N * (compressed ? 1 : 2);
+  Aff<F> p;
+  int st = decode_point(p, bytes + size * i, compressed != 0, checked != 0);
+  st_aff(out + (size_t)AW * i, p);
+  status[i] = (uint8_t)st;
+}
+template <class F>
+__global__ void __launch_bounds__(128) k_encode(const uint64_t* in, int compressed, uint8_t* bytes, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int AW = 2 * FW<F>::W + 1;
+  const size_t size = (size_t)FBytes<F>::N * (compressed ? 1 : 2);
+  Aff<F> p;
+  ld_aff(p, in + (size_t)AW * i);
+  encode_point(bytes + size * i, p, compressed != 0);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Integer-multiply peak microbenchmarks (roofline denominator)
 // ------------------------------------------------------------------------------------------------
 #define PEAK_CHAINS 8
@@ -1273,6 +1299,38 @@ int bls_g1_wnaf_fixed_base_batch(bls_ctx* ctx, const bls_g1* base, int window, c
 int bls_g2_wnaf_fixed_base_batch(bls_ctx* ctx, const bls_g2* base, int window, const bls_fr_repr* k, bls_g2* out, size_t n) { return wnaf_fixed_host(ctx, 2, base, window, k, out, n, nullptr); }
 int bls_g1_wnaf_table(bls_ctx* ctx, const bls_g1* base, int window, bls_g1* table) { return wnaf_fixed_host(ctx, 1, base, window, nullptr, nullptr, 0, table); }
 int bls_g2_wnaf_table(bls_ctx* ctx, const bls_g2* base, int window, bls_g2* table) { return wnaf_fixed_host(ctx, 2, base, window, nullptr, nullptr, 0, table); }
+
+static int codec_host(bls_ctx* ctx, int degree, bool decode, const void* in, int compressed, int checked, void* out, uint8_t* status, size_t n) {
+  if (!ctx || (n && (!in || !out || (decode && !status)))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  const size_t ab = degree == 2 ? sizeof(bls_g2_affine) : sizeof(bls_g1_affine);
+  const size_t eb = (size_t)(degree == 2 ? 96 : 48) * (compressed ? 1 : 2);
+  if (decode) {
+    H2D(din, in, n * eb);
+    DALLOC(dout, n * ab);
+    DALLOC(dst, n);
+    if (degree == 2) k_decode<Fp2><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint8_t*)din.p, compressed, checked, (uint64_t*)dout.p, (uint8_t*)dst.p, n);
+    else k_decode<Fp><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint8_t*)din.p, compressed, checked, (uint64_t*)dout.p, (uint8_t*)dst.p, n);
+    LAUNCH_CHECK();
+    D2H(out, dout, n * ab);
+    D2H(status, dst, n);
+    SYNC();
+  } else {
+    H2D(din, in, n * ab);
+    DALLOC(dout, n * eb);
+    if (degree == 2) k_encode<Fp2><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)din.p, compressed, (uint8_t*)dout.p, n);
+    else k_encode<Fp><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)din.p, compressed, (uint8_t*)dout.p, n);
+    LAUNCH_CHECK();
+    D2H(out, dout, n * eb);
+    SYNC();
+  }
+  return BLS_OK;
+}
+int bls_g1_decode_batch(bls_ctx* ctx, const uint8_t* bytes, int compressed, int checked, bls_g1_affine* out, uint8_t* status, size_t n) { return codec_host(ctx, 1, true, bytes, compressed, checked, out, status, n); }
+int bls_g2_decode_batch(bls_ctx* ctx, const uint8_t* bytes, int compressed, int checked, bls_g2_affine* out, uint8_t* status, size_t n) { return codec_host(ctx, 2, true, bytes, compressed, checked, out, status, n); }
+int bls_g1_encode_batch(bls_ctx* ctx, const bls_g1_affine* in, int compressed, uint8_t* bytes, size_t n) { return codec_host(ctx, 1, false, in, compressed, 0, bytes, nullptr, n); }
+int bls_g2_encode_batch(bls_ctx* ctx, const bls_g2_affine* in, int compressed, uint8_t* bytes, size_t n) { return codec_host(ctx, 2, false, in, compressed, 0, bytes, nullptr, n); }
 
 static int bn_host(bls_ctx* ctx, int degree, void* inout, size_t n) {
   if (!ctx || (n && !inout)) return BLS_ERR_INVALID_ARGUMENT;

@@ -146,6 +146,34 @@ class G1Affine:
     def pairing_with(p, q, ctx=None):
         return Bls12.pairing(p, q, ctx)
 
+    # CurveAffine::into_compressed / into_uncompressed (lib.rs:226-233 -> EncodedPoint::from_affine)
+    @staticmethod
+    def into_compressed(p, ctx=None): return _ctx(ctx).encode(False, p, True)
+    @staticmethod
+    def into_uncompressed(p, ctx=None): return _ctx(ctx).encode(False, p, False)
+
+
+class _Encoded:
+    """EncodedPoint (lib.rs:236-263): `into_affine` checks curve + subgroup membership, `into_affine_unchecked`
+    does not.  Batch-shaped: returns (affine rows, status) with status[i] = 0 for Ok, else the code of the
+    reference's GroupDecodingError (include/pairing_b200.h, BLS_DEC_*)."""
+    _g2, _compressed = False, False
+
+    @classmethod
+    def size(cls): return (96 if cls._g2 else 48) * (1 if cls._compressed else 2)
+    @classmethod
+    def into_affine(cls, data, ctx=None): return _ctx(ctx).decode(cls._g2, data, cls._compressed, True)
+    @classmethod
+    def into_affine_unchecked(cls, data, ctx=None): return _ctx(ctx).decode(cls._g2, data, cls._compressed, False)
+    @classmethod
+    def from_affine(cls, affine, ctx=None): return _ctx(ctx).encode(cls._g2, affine, cls._compressed)
+
+
+class G1Uncompressed(_Encoded): _g2, _compressed = False, False
+class G1Compressed(_Encoded): _g2, _compressed = False, True
+class G2Uncompressed(_Encoded): _g2, _compressed = True, False
+class G2Compressed(_Encoded): _g2, _compressed = True, True
+
 
 class G2Affine:
     @staticmethod
@@ -167,6 +195,11 @@ class G2Affine:
     @staticmethod
     def pairing_with(q, p, ctx=None):
         return Bls12.pairing(p, q, ctx)
+
+    @staticmethod
+    def into_compressed(q, ctx=None): return _ctx(ctx).encode(True, q, True)
+    @staticmethod
+    def into_uncompressed(q, ctx=None): return _ctx(ctx).encode(True, q, False)
 
 
 # Montgomery one, R = 2^384 mod q (fq.rs:22-30)

@@ -30,6 +30,10 @@ extern "C" {
     pub fn bls_multi_miller_loop_prepared(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_prepared, n: usize, out1: *mut bls_fq12) -> c_int;
     pub fn bls_final_exponentiation_batch(ctx: *mut bls_ctx, input: *const bls_fq12, out: *mut bls_fq12, is_some: *mut u8, n: usize) -> c_int;
     pub fn bls_pairing_batch(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_affine, out: *mut bls_fq12, n: usize) -> c_int;
+    pub fn bls_g1_decode_batch(ctx: *mut bls_ctx, bytes: *const u8, compressed: c_int, checked: c_int, out: *mut bls_g1_affine, status: *mut u8, n: usize) -> c_int;
+    pub fn bls_g2_decode_batch(ctx: *mut bls_ctx, bytes: *const u8, compressed: c_int, checked: c_int, out: *mut bls_g2_affine, status: *mut u8, n: usize) -> c_int;
+    pub fn bls_g1_encode_batch(ctx: *mut bls_ctx, input: *const bls_g1_affine, compressed: c_int, bytes: *mut u8, n: usize) -> c_int;
+    pub fn bls_g2_encode_batch(ctx: *mut bls_ctx, input: *const bls_g2_affine, compressed: c_int, bytes: *mut u8, n: usize) -> c_int;
     pub fn bls_fq12_pow_batch(ctx: *mut bls_ctx, a: *const bls_fq12, k: *const bls_fr_repr, out: *mut bls_fq12, n: usize) -> c_int;
     pub fn bls_fq12_product(ctx: *mut bls_ctx, input: *const bls_fq12, n: usize, out1: *mut bls_fq12) -> c_int;
 

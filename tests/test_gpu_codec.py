@@ -1,0 +1,114 @@
+"""GPU point decoding / encoding against the reference's own vector files (k*G for
+k = 0..999, compressed and uncompressed, bls12_381/tests/*.dat) and against the big-int model on the
+reference's invalid-vector cases (bls12_381/tests/mod.rs:99-611)."""
+import os
+
+import numpy as np
+import pytest
+
+import bls_model as m
+import oracle_lib as o
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TH = o.default_threads()
+
+
+def _aff_rows(pts, g2):
+    """model affine points -> ABI rows (Montgomery limbs + infinity word)"""
+    rows = np.zeros((len(pts), 25 if g2 else 13), dtype=np.uint64)
+    for i, (x, y, inf) in enumerate(pts):
+        vals = ([x[0], x[1], y[0], y[1]] if g2 else [x, y])
+        for j, v in enumerate(vals):
+            rows[i, 6 * j:6 * j + 6] = np.array(m.limbs64(m.to_mont(v)), dtype=np.uint64)
+        rows[i, -1] = 1 if inf else 0
+    return rows
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_generator_multiples_vectors(ctx, g2):
+    """decode(entry k) == k*G for all 1000 entries (checked decoding: curve + subgroup), re-encoding reproduces the
+    files byte for byte, and compressed and uncompressed decodings agree."""
+    name = "g2" if g2 else "g1"
+    bu = open(os.path.join(GOLD, name + "_uncompressed_multiples.bin"), "rb").read()
+    bc = open(os.path.join(GOLD, name + "_compressed_multiples.bin"), "rb").read()
+    au, su = ctx.decode(g2, bu, compressed=False, checked=True)
+    ac, sc = ctx.decode(g2, bc, compressed=True, checked=True)
+    assert not su.any() and not sc.any()
+    assert np.array_equal(au, ac) and au.shape[0] == 1000
+    # k*G from the oracle: running projective sum, then into_affine
+    g1a, g2a = o.generators()
+    one = (o.g2_from_affine if g2 else o.g1_from_affine)(g2a if g2 else g1a)
+    w = 36 if g2 else 18
+    acc = np.zeros((1, w), dtype=np.uint64)
+    acc[0, w // 3:w // 3 + 6] = np.array(m.limbs64(m.MONT_R), dtype=np.uint64)
+    pts = np.zeros((1000, w), dtype=np.uint64)
+    for k in range(1000):
+        pts[k] = acc[0]
+        acc = (o.g2_op if g2 else o.g1_op)("add", acc, one)
+    assert np.array_equal(au, (o.g2_into_affine if g2 else o.g1_into_affine)(pts))
+    assert ctx.encode(g2, au, compressed=False) == bu
+    assert ctx.encode(g2, au, compressed=True) == bc
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_invalid_encodings_match_model(ctx, g2):
+    """every malformed encoding of bls12_381/tests/mod.rs:99-611 (+ a few more) gets the model's status, i.e. the
+    reference's GroupDecodingError, checked and unchecked."""
+    gen = m.G2_GEN_AFFINE if g2 else m.G1_GEN_AFFINE
+    qb = m.Q.to_bytes(48, "big")
+    for compressed in (False, True):
+        size = (96 if g2 else 48) * (1 if compressed else 2)
+        z = bytearray(m.encode_point(m._affine_zero(g2), g2, compressed))
+        g = bytearray(m.encode_point(gen, g2, compressed))
+        cases = [bytes(z), bytes(g)]
+        for src in (z, g):
+            for bit in (0x80, 0x40, 0x20):
+                c = bytearray(src); c[0] ^= bit; cases.append(bytes(c))
+        for i in range(size):
+            c = bytearray(z); c[i] |= 1; cases.append(bytes(c))
+        for slot in range(size // 48):
+            c = bytearray(g); c[48 * slot:48 * slot + 48] = qb
+            if compressed:
+                c[0] |= 0x80
+            cases.append(bytes(c))
+            c2 = bytearray(c); c2[48 * slot + 47] ^= 1; cases.append(bytes(c2))      # q - 1 (or q + 1 with flags): valid integer
+        # small x values: on the curve or not, in the subgroup or not (tests/mod.rs:190-219, 418-470)
+        for v in range(0, 12):
+            x = (v, 0) if g2 else v
+            p = m.get_point_from_x(x, bool(v & 1), g2)
+            if p is not None:
+                cases.append(m.encode_point(p, g2, compressed))
+            elif compressed:
+                c = bytearray((x[1].to_bytes(48, "big") + x[0].to_bytes(48, "big")) if g2 else x.to_bytes(48, "big")); c[0] |= 0x80
+                cases.append(bytes(c))
+            else:
+                y = m.G2_GEN_AFFINE[1] if g2 else m.G1_GEN_AFFINE[1]
+                cases.append(m.encode_point((x, y, False), g2, False))
+        blob = b"".join(cases)
+        for checked in (True, False):
+            aff, status = ctx.decode(g2, blob, compressed, checked)
+            want = [m.decode_point(c, g2, compressed, checked) for c in cases]
+            assert status.tolist() == [w[0] for w in want], (compressed, checked)
+            good = [i for i, w in enumerate(want) if w[0] == 0]
+            assert np.array_equal(aff[good], _aff_rows([want[i][1] for i in good], g2))
+            assert set(status.tolist()) >= ({0, 1, 2, 3, 4} if checked else {0, 1, 2, 3}) - ({3} if (not compressed and not checked) else set())
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_encode_decode_round_trip_random(ctx, g2):
+    import datagen as dg
+    n = 300
+    aff = (dg.g2_affine_points if g2 else dg.g1_affine_points)(n, 91, infinity_at=(7,))
+    for compressed in (False, True):
+        enc = ctx.encode(g2, aff, compressed)
+        back, status = ctx.decode(g2, enc, compressed, checked=True)
+        assert not status.any() and np.array_equal(back, aff)
+    # the greatest-y flag: negating y flips bit 5 of the compressed form and nothing else
+    neg = aff.copy()
+    negated = (o.g2_op if g2 else o.g1_op)("negate", (o.g2_from_affine if g2 else o.g1_from_affine)(aff))
+    neg = (o.g2_into_affine if g2 else o.g1_into_affine)(negated)
+    e1 = np.frombuffer(ctx.encode(g2, aff, True), dtype=np.uint8).reshape(n, -1)
+    e2 = np.frombuffer(ctx.encode(g2, neg, True), dtype=np.uint8).reshape(n, -1)
+    live = aff[:, -1] == 0
+    assert np.array_equal(e1[live][:, 1:], e2[live][:, 1:]) and np.all((e1[live][:, 0] ^ e2[live][:, 0]) == 0x20)

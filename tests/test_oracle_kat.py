@@ -269,3 +269,78 @@ def test_generator_multiples_vectors(g2):
         got_c += _enc_compressed(pt, g2)
     assert bytes(got_u) == want_u
     assert bytes(got_c) == want_c
+
+
+# ---- point encodings: the model's decode/encode against the reference's own vectors
+@pytest.mark.parametrize("g2", [False, True])
+def test_model_decodes_and_encodes_generator_multiples(g2):
+    """tests/mod.rs:55-97 read the other way: decoding entry k of the .dat files gives k*G (checked decoding
+    passes: on the curve and in the subgroup for a sample), and re-encoding gives the bytes back."""
+    F = m._F2 if g2 else m._F1
+    name = "g2" if g2 else "g1"
+    us = 192 if g2 else 96
+    cs = us // 2
+    want_u = open(os.path.join(GOLD, name + "_uncompressed_multiples.bin"), "rb").read()
+    want_c = open(os.path.join(GOLD, name + "_compressed_multiples.bin"), "rb").read()
+    e = m.pt_zero(F)
+    gen = m.pt_from_affine(F, m.G2_GEN_AFFINE if g2 else m.G1_GEN_AFFINE)
+    for k in range(120):
+        aff = m.pt_to_affine(F, e)
+        bu, bc = want_u[us * k:us * k + us], want_c[cs * k:cs * k + cs]
+        checked = k < 6                                   # the subgroup check is a 255-bit scalar multiplication
+        assert m.decode_point(bu, g2, False, checked) == (m.DEC_OK, aff)
+        assert m.decode_point(bc, g2, True, checked) == (m.DEC_OK, aff)
+        assert m.encode_point(aff, g2, False) == bu and m.encode_point(aff, g2, True) == bc
+        e = m.pt_add(F, e, gen)
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_model_rejects_invalid_encodings(g2):
+    """bls12_381/tests/mod.rs:99-611 restated: every malformed encoding gets the reference's error."""
+    us = 192 if g2 else 96
+    gen = m.G2_GEN_AFFINE if g2 else m.G1_GEN_AFFINE
+    for compressed in (False, True):
+        size = us // 2 if compressed else us
+        z = bytearray(m.encode_point(m._affine_zero(g2), g2, compressed))
+        o_ = bytearray(m.encode_point(gen, g2, compressed))
+        flip = lambda b, i, v: bytes(b[:i]) + bytes([b[i] ^ v]) + bytes(b[i + 1:])
+        assert m.decode_point(flip(z, 0, 0x80), g2, compressed)[0] == m.DEC_UNEXPECTED_COMPRESSION_MODE
+        assert m.decode_point(flip(o_, 0, 0x80), g2, compressed)[0] == m.DEC_UNEXPECTED_COMPRESSION_MODE
+        assert m.decode_point(flip(z, 0, 0x20), g2, compressed)[0] == m.DEC_UNEXPECTED_INFORMATION
+        for i in range(size):
+            bad = bytearray(z); bad[i] |= 1
+            assert m.decode_point(bytes(bad), g2, compressed)[0] == m.DEC_UNEXPECTED_INFORMATION
+        qb = m.Q.to_bytes(48, "big")
+        flags = bytes([o_[0] & 0xe0])
+        ncoord = size // 48
+        for slot in range(ncoord):                          # Fq::char() written over one coordinate
+            bad = bytearray(o_); bad[48 * slot:48 * slot + 48] = qb
+            if slot == 0:
+                bad[0] |= flags[0] & 0x80                   # keep the compression flag as the reference's write_be does not
+            st = m.decode_point(bytes(bad), g2, compressed)[0]
+            idx = slot if not g2 else [1, 0, 3, 2][slot]    # G2 bytes are c1 then c0
+            assert st == m.DEC_COORDINATE + idx, (compressed, slot, st)
+        # not on the curve: uncompressed x := 0 with the generator's y (tests/mod.rs:172-188); compressed: the first
+        # x = 1, 2, ... whose x^3 + b has no square root (tests/mod.rs:418-440)
+        bad = bytearray(o_)
+        if compressed:
+            x = (1, 0) if g2 else 1
+            while m.get_point_from_x(x, False, g2) is not None:
+                x = m.fq2_add(x, m.FQ2_ONE) if g2 else x + 1
+            bad[:] = (x[1].to_bytes(48, "big") + x[0].to_bytes(48, "big")) if g2 else x.to_bytes(48, "big")
+            bad[0] |= 0x80
+        else:
+            bad[0:48 * (2 if g2 else 1)] = bytes(48 * (2 if g2 else 1))
+        assert m.decode_point(bytes(bad), g2, compressed)[0] == m.DEC_NOT_ON_CURVE
+    # a point on the curve but outside the r-order subgroup (tests/mod.rs:190-219): first x = 1, 2, ... with a root
+    x = (1, 0) if g2 else 1
+    while True:
+        p = m.get_point_from_x(x, False, g2)
+        if p is not None:
+            break
+        x = m.fq2_add(x, m.FQ2_ONE) if g2 else x + 1
+    assert m.is_on_curve(p, g2) and not m.is_in_correct_subgroup_assuming_on_curve(p, g2)
+    for compressed in (False, True):
+        enc = m.encode_point(p, g2, compressed)
+        assert m.decode_point(enc, g2, compressed, checked=False) == (m.DEC_OK, p)
+        assert m.decode_point(enc, g2, compressed)[0] == m.DEC_NOT_IN_SUBGROUP
