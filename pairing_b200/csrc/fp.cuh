@@ -184,6 +184,29 @@ __device__ __forceinline__ Fp fp_neg(const Fp& a) {
   return r;
 }
 
+// q - a without the zero special case: the result is in (0, q], i.e. q itself for a == 0.  Only for a value
+// that is consumed as one factor of fp_mul2 (whose bound x*bx + y*by < 2 q^2 still holds with y == q).
+__device__ __forceinline__ Fp fp_neg_noncanonical(const Fp& a) {
+  Fp r;
+  asm("sub.cc.u32 %0, " BLS_STR(BLS_Q0) ", %12;\n\t"
+      "subc.cc.u32 %1, " BLS_STR(BLS_Q1) ", %13;\n\t"
+      "subc.cc.u32 %2, " BLS_STR(BLS_Q2) ", %14;\n\t"
+      "subc.cc.u32 %3, " BLS_STR(BLS_Q3) ", %15;\n\t"
+      "subc.cc.u32 %4, " BLS_STR(BLS_Q4) ", %16;\n\t"
+      "subc.cc.u32 %5, " BLS_STR(BLS_Q5) ", %17;\n\t"
+      "subc.cc.u32 %6, " BLS_STR(BLS_Q6) ", %18;\n\t"
+      "subc.cc.u32 %7, " BLS_STR(BLS_Q7) ", %19;\n\t"
+      "subc.cc.u32 %8, " BLS_STR(BLS_Q8) ", %20;\n\t"
+      "subc.cc.u32 %9, " BLS_STR(BLS_Q9) ", %21;\n\t"
+      "subc.cc.u32 %10, " BLS_STR(BLS_Q10) ", %22;\n\t"
+      "subc.u32 %11, " BLS_STR(BLS_Q11) ", %23;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+        "=r"(r.v[7]), "=r"(r.v[8]), "=r"(r.v[9]), "=r"(r.v[10]), "=r"(r.v[11])
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+        "r"(a.v[7]), "r"(a.v[8]), "r"(a.v[9]), "r"(a.v[10]), "r"(a.v[11]));
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Montgomery product building blocks.  Two 12-word accumulators: `e` aligned with word 0 of the
 // running total and `o` aligned with word 1 (total = e + (o << 32)).
@@ -369,6 +392,6 @@ __device__ __forceinline__ Fp fp_mul2_inline(const Fp& x, const Fp& bx, const Fp
 
 __device__ __noinline__ Fp fp_mul(Fp a, Fp b) { return fp_mul_inline(a, b); }
 __device__ __noinline__ Fp fp_mul2(Fp x, Fp bx, Fp y, Fp by) { return fp_mul2_inline(x, bx, y, by); }
-__device__ __noinline__ Fp fp_sqr(Fp a) { return fp_mul_inline(a, a); }
+__device__ __forceinline__ Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }   // one copy of the product code (instruction-cache footprint)
 
 }  // namespace bls

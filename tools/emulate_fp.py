@@ -108,7 +108,8 @@ if __name__ == "__main__":
     for a, b in cases:
         assert fp_mul(a, b) == a * b * RI % m.Q
     print("fp_mul: %d cases ok" % len(cases))
-    cases4 = [(a, b, c, d) for a in edge for b in edge for c in (0, m.Q - 1) for d in (1, m.Q - 1)]
+    # third operand y may be q itself: p2_mul passes q - a1 without the zero special case (fp_neg_noncanonical)
+    cases4 = [(a, b, c, d) for a in edge for b in edge for c in (0, m.Q - 1, m.Q) for d in (1, m.Q - 1)]
     cases4 += [tuple(random.randrange(m.Q) for _ in range(4)) for _ in range(3000)]
     for a, b, c, d in cases4:
         assert fp_mul2(a, b, c, d) == (a * b + c * d) * RI % m.Q
