@@ -44,11 +44,11 @@ __device__ __forceinline__ void fp_to_be(uint8_t* b, const Fp& a) {
 // Fq::from_repr validity (fq.rs:747-756): the integer is < q
 __device__ __forceinline__ bool fp_repr_is_valid(const Fp& a) {
   Fp t = a;
-  fp_final_sub(t);          // a < 2^384 < 10 q, so "unchanged by one conditional subtraction" <=> a < q
-  return fp_eq(t, a);
+  fp_final_sub(t);          // "unchanged by one conditional subtraction" <=> a < q
+  return fp_eq_raw(t, a);
 }
 __device__ __forceinline__ Fp fp_to_mont(const Fp& raw) { return fp_mul(raw, fp_r2()); }
-__device__ __forceinline__ Fp fp_from_mont(const Fp& a) { Fp one = fp_zero(); one.v[0] = 1; return fp_mul(a, one); }   // into_repr, fq.rs:758-777
+__device__ __forceinline__ Fp fp_from_mont(const Fp& a) { Fp one = fp_zero(); one.v[0] = 1; return fp_canon(fp_mul(a, one)); }   // into_repr, fq.rs:758-777
 // integer comparison of two canonical integers: a > b
 __device__ __forceinline__ bool fp_repr_gt(const Fp& a, const Fp& b) {
 #pragma unroll
@@ -62,7 +62,7 @@ __device__ __forceinline__ bool f_gt(const Fp& a, const Fp& b) { return fp_repr_
 // Ord for Fq2 (fq2.rs:20-31): c1 first, then c0
 __device__ __forceinline__ bool f_gt(const Fp2& a, const Fp2& b) {
   Fp a1 = fp_from_mont(a.c1), b1 = fp_from_mont(b.c1);
-  if (!fp_eq(a1, b1)) return fp_repr_gt(a1, b1);
+  if (!fp_eq_raw(a1, b1)) return fp_repr_gt(a1, b1);
   return fp_repr_gt(fp_from_mont(a.c0), fp_from_mont(b.c0));
 }
 

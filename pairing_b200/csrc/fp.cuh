@@ -1,7 +1,17 @@
 // fp.cuh -- Fq (the 381-bit BLS12-381 base field) on sm_100a: 12 x 32-bit limbs in registers,
-// Montgomery form (x * 2^384 mod q), every public result canonical (< q) so that "bit-exact" and
-// "same field value" coincide (reference: bls12_381/fq.rs:796-1123; the reference works on 6 x u64
+// Montgomery form (x * 2^384 mod q) (reference: bls12_381/fq.rs:796-1123; the reference works on 6 x u64
 // limbs -- byte-for-byte the same little-endian layout).
+//
+// Register values live in the RELAXED range [0, 2q] (2q < 2^382): every routine accepts and returns
+// representatives in that range, and the value is made canonical (< q, the reference's representation) only
+// where bits are observable -- stores to ABI memory (st_fp in kernels.cu), equality and zero tests.  That
+// removes the conditional subtraction (13 carry-linked subtractions + 12 selects, a serial tail) from every
+// Montgomery product and the zero test from every negation:
+//   product of a, b <= 2q:  a b / R + q  <=  4 q^2 / R + q  <  1.41 q        (q / R < 0.1021)
+//   dual product:           (x bx + y by) / R + q  <=  8 q^2 / R + q  <  1.82 q
+//   add: a + b <= 4q, minus 2q if >= 2q;  sub: a - b, plus 2q if negative;  neg: 2q - a
+// tools/emulate_fp.py replays the exact carry schedule on operands up to 2q and checks both the bounds and
+// that every carry the PTX drops is zero.
 //
 // Multiplication is a word-serial (CIOS) Montgomery product on 32-bit limbs whose partial products
 // are accumulated in two independent 12-word carry chains -- products of even-indexed limbs and of
@@ -30,6 +40,19 @@ struct Fp { uint32_t v[12]; };
 #define BLS_Q10 0x397fe69a
 #define BLS_Q11 0x1a0111ea
 #define BLS_NINV 0xfffcfffdu
+// 2q
+#define BLS_2Q0 0xffff5556
+#define BLS_2Q1 0x73fdffff
+#define BLS_2Q2 0x62a7ffff
+#define BLS_2Q3 0x3d57fffd
+#define BLS_2Q4 0xed61ec48
+#define BLS_2Q5 0xce61a541
+#define BLS_2Q6 0xe70a257e
+#define BLS_2Q7 0xc8ee9709
+#define BLS_2Q8 0x869759ae
+#define BLS_2Q9 0x96374f6c
+#define BLS_2Q10 0x72ffcd34
+#define BLS_2Q11 0x340223d4
 #define BLS_STR2(x) #x
 #define BLS_STR(x) BLS_STR2(x)
 
@@ -48,20 +71,21 @@ __device__ __forceinline__ Fp fp_r2() {
              0x939d83c0u, 0x67eb88a9u, 0xb519952du, 0x9a793e85u, 0x92cae3aau, 0x11988fe5u}};
 }
 
-__device__ __forceinline__ bool fp_is_zero(const Fp& a) {
+// bit-pattern tests (for canonical values and raw integers)
+__device__ __forceinline__ bool fp_is_zero_raw(const Fp& a) {
   uint32_t o = a.v[0];
 #pragma unroll
   for (int i = 1; i < 12; i++) o |= a.v[i];
   return o == 0;
 }
-__device__ __forceinline__ bool fp_eq(const Fp& a, const Fp& b) {
+__device__ __forceinline__ bool fp_eq_raw(const Fp& a, const Fp& b) {
   uint32_t o = a.v[0] ^ b.v[0];
 #pragma unroll
   for (int i = 1; i < 12; i++) o |= a.v[i] ^ b.v[i];
   return o == 0;
 }
 
-// r = a - q if a >= q else a   (fq.rs:1030-1034 `reduce`); a < 2q < 2^384
+// r = a - q if a >= q else a   (fq.rs:1030-1034 `reduce`)
 __device__ __forceinline__ void fp_final_sub(Fp& a) {
   uint32_t t[12], borrow;
   asm("sub.cc.u32 %0, %13, " BLS_STR(BLS_Q0) ";\n\t"
@@ -86,7 +110,41 @@ __device__ __forceinline__ void fp_final_sub(Fp& a) {
   for (int i = 0; i < 12; i++) a.v[i] = borrow ? a.v[i] : t[i];
 }
 
-// fq.rs:813-819 add_assign: a + b then conditional subtract.  a, b < q.
+// the canonical representative (< q) of a value in [0, 2q]
+__device__ __forceinline__ Fp fp_canon(const Fp& a) {
+  Fp r = a;
+  fp_final_sub(r);
+  fp_final_sub(r);
+  return r;
+}
+__device__ __forceinline__ bool fp_is_zero(const Fp& a) { return fp_is_zero_raw(fp_canon(a)); }
+__device__ __forceinline__ bool fp_eq(const Fp& a, const Fp& b) { return fp_eq_raw(fp_canon(a), fp_canon(b)); }
+
+// r = a - 2q if a >= 2q else a;  a <= 4q < 2^384
+__device__ __forceinline__ void fp_cond_sub_2q(Fp& a) {
+  uint32_t t[12], borrow;
+  asm("sub.cc.u32 %0, %13, " BLS_STR(BLS_2Q0) ";\n\t"
+      "subc.cc.u32 %1, %14, " BLS_STR(BLS_2Q1) ";\n\t"
+      "subc.cc.u32 %2, %15, " BLS_STR(BLS_2Q2) ";\n\t"
+      "subc.cc.u32 %3, %16, " BLS_STR(BLS_2Q3) ";\n\t"
+      "subc.cc.u32 %4, %17, " BLS_STR(BLS_2Q4) ";\n\t"
+      "subc.cc.u32 %5, %18, " BLS_STR(BLS_2Q5) ";\n\t"
+      "subc.cc.u32 %6, %19, " BLS_STR(BLS_2Q6) ";\n\t"
+      "subc.cc.u32 %7, %20, " BLS_STR(BLS_2Q7) ";\n\t"
+      "subc.cc.u32 %8, %21, " BLS_STR(BLS_2Q8) ";\n\t"
+      "subc.cc.u32 %9, %22, " BLS_STR(BLS_2Q9) ";\n\t"
+      "subc.cc.u32 %10, %23, " BLS_STR(BLS_2Q10) ";\n\t"
+      "subc.cc.u32 %11, %24, " BLS_STR(BLS_2Q11) ";\n\t"
+      "subc.u32 %12, 0, 0;"
+      : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]),
+        "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(borrow)
+      : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
+        "r"(a.v[7]), "r"(a.v[8]), "r"(a.v[9]), "r"(a.v[10]), "r"(a.v[11]));
+#pragma unroll
+  for (int i = 0; i < 12; i++) a.v[i] = borrow ? a.v[i] : t[i];
+}
+
+// fq.rs:813-819 add_assign.  a, b <= 2q -> result <= 2q.
 __device__ __forceinline__ Fp fp_add(const Fp& a, const Fp& b) {
   Fp r;
   asm("add.cc.u32 %0, %12, %24;\n\t"
@@ -107,14 +165,14 @@ __device__ __forceinline__ Fp fp_add(const Fp& a, const Fp& b) {
         "r"(a.v[7]), "r"(a.v[8]), "r"(a.v[9]), "r"(a.v[10]), "r"(a.v[11]),
         "r"(b.v[0]), "r"(b.v[1]), "r"(b.v[2]), "r"(b.v[3]), "r"(b.v[4]), "r"(b.v[5]), "r"(b.v[6]),
         "r"(b.v[7]), "r"(b.v[8]), "r"(b.v[9]), "r"(b.v[10]), "r"(b.v[11]));
-  fp_final_sub(r);
+  fp_cond_sub_2q(r);
   return r;
 }
 
 // fq.rs:822-828 double
 __device__ __forceinline__ Fp fp_dbl(const Fp& a) { return fp_add(a, a); }
 
-// fq.rs:831-838 sub_assign: a - b, adding q back when it borrows.  a, b < q.
+// fq.rs:831-838 sub_assign: a - b, adding 2q back when it borrows.  a, b <= 2q -> result <= 2q.
 __device__ __forceinline__ Fp fp_sub(const Fp& a, const Fp& b) {
   Fp r;
   uint32_t borrow;
@@ -152,54 +210,28 @@ __device__ __forceinline__ Fp fp_sub(const Fp& a, const Fp& b) {
       "addc.u32 %11, %11, %23;"
       : "+r"(r.v[0]), "+r"(r.v[1]), "+r"(r.v[2]), "+r"(r.v[3]), "+r"(r.v[4]), "+r"(r.v[5]), "+r"(r.v[6]),
         "+r"(r.v[7]), "+r"(r.v[8]), "+r"(r.v[9]), "+r"(r.v[10]), "+r"(r.v[11])
-      : "r"(BLS_Q0 & borrow), "r"(BLS_Q1 & borrow), "r"(BLS_Q2 & borrow), "r"(BLS_Q3 & borrow),
-        "r"(BLS_Q4 & borrow), "r"(BLS_Q5 & borrow), "r"(BLS_Q6 & borrow), "r"(BLS_Q7 & borrow),
-        "r"(BLS_Q8 & borrow), "r"(BLS_Q9 & borrow), "r"(BLS_Q10 & borrow), "r"(BLS_Q11 & borrow));
+      : "r"(BLS_2Q0 & borrow), "r"(BLS_2Q1 & borrow), "r"(BLS_2Q2 & borrow), "r"(BLS_2Q3 & borrow),
+        "r"(BLS_2Q4 & borrow), "r"(BLS_2Q5 & borrow), "r"(BLS_2Q6 & borrow), "r"(BLS_2Q7 & borrow),
+        "r"(BLS_2Q8 & borrow), "r"(BLS_2Q9 & borrow), "r"(BLS_2Q10 & borrow), "r"(BLS_2Q11 & borrow));
   return r;
 }
 
-// fq.rs:841-847 negate: q - a, except 0 -> 0
+// fq.rs:841-847 negate: 2q - a (a <= 2q -> result <= 2q; the reference's 0 -> 0 special case is a matter of the
+// canonical representative only: 2q is 0)
 __device__ __forceinline__ Fp fp_neg(const Fp& a) {
-  uint32_t nz = fp_is_zero(a) ? 0u : 0xffffffffu;
   Fp r;
-  asm("sub.cc.u32 %0, %12, %24;\n\t"
-      "subc.cc.u32 %1, %13, %25;\n\t"
-      "subc.cc.u32 %2, %14, %26;\n\t"
-      "subc.cc.u32 %3, %15, %27;\n\t"
-      "subc.cc.u32 %4, %16, %28;\n\t"
-      "subc.cc.u32 %5, %17, %29;\n\t"
-      "subc.cc.u32 %6, %18, %30;\n\t"
-      "subc.cc.u32 %7, %19, %31;\n\t"
-      "subc.cc.u32 %8, %20, %32;\n\t"
-      "subc.cc.u32 %9, %21, %33;\n\t"
-      "subc.cc.u32 %10, %22, %34;\n\t"
-      "subc.u32 %11, %23, %35;"
-      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
-        "=r"(r.v[7]), "=r"(r.v[8]), "=r"(r.v[9]), "=r"(r.v[10]), "=r"(r.v[11])
-      : "r"(BLS_Q0 & nz), "r"(BLS_Q1 & nz), "r"(BLS_Q2 & nz), "r"(BLS_Q3 & nz), "r"(BLS_Q4 & nz),
-        "r"(BLS_Q5 & nz), "r"(BLS_Q6 & nz), "r"(BLS_Q7 & nz), "r"(BLS_Q8 & nz), "r"(BLS_Q9 & nz),
-        "r"(BLS_Q10 & nz), "r"(BLS_Q11 & nz),
-        "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
-        "r"(a.v[7]), "r"(a.v[8]), "r"(a.v[9]), "r"(a.v[10]), "r"(a.v[11]));
-  return r;
-}
-
-// q - a without the zero special case: the result is in (0, q], i.e. q itself for a == 0.  Only for a value
-// that is consumed as one factor of fp_mul2 (whose bound x*bx + y*by < 2 q^2 still holds with y == q).
-__device__ __forceinline__ Fp fp_neg_noncanonical(const Fp& a) {
-  Fp r;
-  asm("sub.cc.u32 %0, " BLS_STR(BLS_Q0) ", %12;\n\t"
-      "subc.cc.u32 %1, " BLS_STR(BLS_Q1) ", %13;\n\t"
-      "subc.cc.u32 %2, " BLS_STR(BLS_Q2) ", %14;\n\t"
-      "subc.cc.u32 %3, " BLS_STR(BLS_Q3) ", %15;\n\t"
-      "subc.cc.u32 %4, " BLS_STR(BLS_Q4) ", %16;\n\t"
-      "subc.cc.u32 %5, " BLS_STR(BLS_Q5) ", %17;\n\t"
-      "subc.cc.u32 %6, " BLS_STR(BLS_Q6) ", %18;\n\t"
-      "subc.cc.u32 %7, " BLS_STR(BLS_Q7) ", %19;\n\t"
-      "subc.cc.u32 %8, " BLS_STR(BLS_Q8) ", %20;\n\t"
-      "subc.cc.u32 %9, " BLS_STR(BLS_Q9) ", %21;\n\t"
-      "subc.cc.u32 %10, " BLS_STR(BLS_Q10) ", %22;\n\t"
-      "subc.u32 %11, " BLS_STR(BLS_Q11) ", %23;"
+  asm("sub.cc.u32 %0, " BLS_STR(BLS_2Q0) ", %12;\n\t"
+      "subc.cc.u32 %1, " BLS_STR(BLS_2Q1) ", %13;\n\t"
+      "subc.cc.u32 %2, " BLS_STR(BLS_2Q2) ", %14;\n\t"
+      "subc.cc.u32 %3, " BLS_STR(BLS_2Q3) ", %15;\n\t"
+      "subc.cc.u32 %4, " BLS_STR(BLS_2Q4) ", %16;\n\t"
+      "subc.cc.u32 %5, " BLS_STR(BLS_2Q5) ", %17;\n\t"
+      "subc.cc.u32 %6, " BLS_STR(BLS_2Q6) ", %18;\n\t"
+      "subc.cc.u32 %7, " BLS_STR(BLS_2Q7) ", %19;\n\t"
+      "subc.cc.u32 %8, " BLS_STR(BLS_2Q8) ", %20;\n\t"
+      "subc.cc.u32 %9, " BLS_STR(BLS_2Q9) ", %21;\n\t"
+      "subc.cc.u32 %10, " BLS_STR(BLS_2Q10) ", %22;\n\t"
+      "subc.u32 %11, " BLS_STR(BLS_2Q11) ", %23;"
       : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
         "=r"(r.v[7]), "=r"(r.v[8]), "=r"(r.v[9]), "=r"(r.v[10]), "=r"(r.v[11])
       : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]),
@@ -300,7 +332,7 @@ __device__ __forceinline__ void fp_redc_row(uint32_t (&e)[12], uint32_t (&o)[12]
   fp_cmad_q_even(e, m, o[11]);
 }
 
-// r = (e >> 32) + o, then conditional subtract
+// r = (e >> 32) + o  (<= 2q by the bounds in the header: no conditional subtraction)
 __device__ __forceinline__ Fp fp_merge(const uint32_t (&e)[12], const uint32_t (&o)[12]) {
   Fp r;
   asm("add.cc.u32 %0, %12, %23;\n\t"
@@ -321,7 +353,6 @@ __device__ __forceinline__ Fp fp_merge(const uint32_t (&e)[12], const uint32_t (
         "r"(e[10]), "r"(e[11]),
         "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]), "r"(o[8]),
         "r"(o[9]), "r"(o[10]), "r"(o[11]));
-  fp_final_sub(r);
   return r;
 }
 
@@ -354,8 +385,8 @@ __device__ __forceinline__ Fp fp_mul_inline(const Fp& a, const Fp& b) {
 }
 
 // (x * bx + y * by) * 2^-384 mod q with ONE Montgomery reduction (lazy reduction of a sum of two
-// products): each row accumulates both partial products before the m*q row.  The sum is < 2 q^2, so
-// the result is < q (2q/2^384 + 1) < 1.25 q and one conditional subtraction canonicalises it.
+// products): each row accumulates both partial products before the m*q row.  With all four operands
+// <= 2q the sum is <= 8 q^2 and the result < 1.82 q.
 // Used by the lane-pair Fq2 arithmetic: c0 = a0 b0 + (-a1) b1, c1 = a0 b1 + a1 b0.
 // 288 (products) + 144 (m*q) wide MACs + 12 IMAD = 444 instead of 2 x 300.
 // Carry analysis: tools/emulate_fp.py replays this schedule word by word and asserts that every

@@ -30,7 +30,9 @@ __device__ __forceinline__ Fp ld_fp(const uint64_t* p) {
   for (int i = 0; i < 6; i++) { uint2 t = q[i]; r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
   return r;
 }
-__device__ __forceinline__ void st_fp(uint64_t* p, const Fp& a) {
+// every value that leaves through the ABI is the canonical representative (< q), as in the reference
+__device__ __forceinline__ void st_fp(uint64_t* p, const Fp& x) {
+  const Fp a = fp_canon(x);
   uint2* q = reinterpret_cast<uint2*>(p);
 #pragma unroll
   for (int i = 0; i < 6; i++) q[i] = make_uint2(a.v[2 * i], a.v[2 * i + 1]);
@@ -95,7 +97,7 @@ __global__ void __launch_bounds__(128) k_fq_op(int op, const uint64_t* a, const 
     case BLS_OP_INV: good = fp_inv(r, x); break;
     case BLS_OP_FROM_REPR: {   // fq.rs:747-756: valid iff x < q, then x * R2
       Fp t = x; fp_final_sub(t);
-      good = fp_eq(t, x);
+      good = fp_eq_raw(t, x);
       r = good ? fp_mul(x, fp_r2()) : fp_zero();
       break;
     }

@@ -60,7 +60,7 @@ __device__ __noinline__ P2 p2_mul(P2 a, P2 b) {
   bool c0 = pair_c() == 0;
   // lane 0: a0 * b0 + (-a1) * b1        lane 1: a0 * b1 + a1 * b0   (X * b_own + Y * b_oth)
   Fp x = fp_select(c0, a.v, ao);
-  Fp y = fp_select(c0, fp_neg_noncanonical(ao), a.v);
+  Fp y = fp_select(c0, fp_neg(ao), a.v);
   return P2{fp_mul2(x, b.v, y, bo)};
 }
 // fq2.rs:87-101: c0 = (a0 + a1)(a0 - a1), c1 = 2 a0 a1
