@@ -50,9 +50,8 @@ __device__ __forceinline__ bool p2_is_zero(const P2& a) {
 // x (1 + u) = (c0 - c1) + (c0 + c1) u   (fq2.rs:41-45)
 __device__ __noinline__ P2 p2_mul_by_nonresidue(P2 a) {
   Fp oth = pair_xchg(a.v);
-  Fp d = fp_sub(a.v, oth);      // lane 0: c0 - c1
-  Fp s = fp_add(a.v, oth);      // lane 1: c1 + c0
-  return P2{fp_select(pair_c() == 0, d, s)};
+  // lane 0: c0 - c1 = own + (2q - oth);  lane 1: c1 + c0 = own + oth   (one folded addition instead of add, sub, select)
+  return P2{fp_add(a.v, fp_select(pair_c() == 0, fp_neg(oth), oth))};
 }
 // fq2.rs:123-136: c0 = a0 b0 - a1 b1, c1 = a0 b1 + a1 b0, one lazily reduced dual product per lane
 __device__ __noinline__ P2 p2_mul(P2 a, P2 b) {
