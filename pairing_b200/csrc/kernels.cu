@@ -677,9 +677,12 @@ __global__ void __launch_bounds__(128) k_batch_normalization(uint64_t* pts, size
   F acc = one;
   size_t last = t;
   bool any = false;
+  // forward pass; the next z is loaded before the current product so that the load latency overlaps the arithmetic
+  F znext; ld_F(znext, pts + (size_t)PW * t + 2 * W);
 #pragma unroll 1
   for (size_t i = t; i < n; i += T) {
-    F z; ld_F(z, pts + (size_t)PW * i + 2 * W);
+    const F z = znext;
+    if (i + T < n) ld_F(znext, pts + (size_t)PW * (i + T) + 2 * W);
     last = i;
     if (f_is_zero(z) || f_eq(z, one)) continue;   // is_normalized, ec.rs:242-244
     st_F(scratch + (size_t)W * i, acc);           // product of the previous live z's
@@ -688,21 +691,29 @@ __global__ void __launch_bounds__(128) k_batch_normalization(uint64_t* pts, size
   }
   if (!any) return;
   F inv; f_inv(inv, acc);
+  // backward pass, same prefetching: (z, prefix, x, y) of the next point are in flight during the 6 products
+  F zn, pn, xn, yn;
+  ld_F(zn, pts + (size_t)PW * last + 2 * W); ld_F(pn, scratch + (size_t)W * last);
+  ld_F(xn, pts + (size_t)PW * last); ld_F(yn, pts + (size_t)PW * last + W);
 #pragma unroll 1
   for (size_t i = last;; i -= T) {
     uint64_t* pi = pts + (size_t)PW * i;
-    F z; ld_F(z, pi + 2 * W);
+    const F z = zn, prev = pn, x = xn, y = yn;
+    const bool more = i >= T + t;                 // i == t was the first point of this thread
+    if (more) {
+      const size_t j = i - T;
+      ld_F(zn, pts + (size_t)PW * j + 2 * W); ld_F(pn, scratch + (size_t)W * j);
+      ld_F(xn, pts + (size_t)PW * j); ld_F(yn, pts + (size_t)PW * j + W);
+    }
     if (!(f_is_zero(z) || f_eq(z, one))) {
-      F prev; ld_F(prev, scratch + (size_t)W * i);
       F zinv = f_mul(inv, prev);
       inv = f_mul(inv, z);
       F zz = f_sqr(zinv);
-      F x, y; ld_F(x, pi); ld_F(y, pi + W);
       st_F(pi, f_mul(x, zz));
       st_F(pi + W, f_mul(y, f_mul(zz, zinv)));
       st_F(pi + 2 * W, one);
     }
-    if (i < T + t) break;   // i == t was the first point of this thread
+    if (!more) break;
   }
 }
 
@@ -1073,7 +1084,7 @@ int bls_g2_wnaf_fixed_base_dev(bls_ctx* ctx, const bls_g2* table, int window, co
 // threads for batch normalisation: >= 64 points per thread when n allows it
 static size_t bn_threads(const bls_ctx* ctx, size_t n) {
   size_t t = (n + 63) / 64;
-  size_t cap = (size_t)ctx->sm_count * 8 * TPB;
+  size_t cap = (size_t)ctx->sm_count * 4 * TPB;   // more points per thread for huge batches: the per-thread inversion (476 M) amortises better
   if (t > cap) t = cap;
   t = (t + TPB - 1) / TPB * TPB;
   return t ? t : TPB;
