@@ -1,8 +1,8 @@
 // kernels.cu -- CUDA kernels (sm_100a) and the C ABI of include/pairing_b200.h.
 //
-// Round-1 mapping: one thread per element (pairing, point, field element); field values live in
-// registers at the Fq/Fq2 level (fp_mul / fp2_mul take and return their operands in registers) and
-// in per-thread local memory (L1-resident, lane-interleaved by the hardware) at the Fq6/Fq12 level.
+// Mapping: the pairing engine (Miller loops, final exponentiation, G2Prepared, GT powers) runs on LANE PAIRS
+// (pair_tower.cuh: two lanes per Fq2-valued object); the curve kernels (group law, wNAF, normalisation,
+// encodings) and the field-op test kernels run one thread per element (tower.cuh, curve.cuh).
 // Inputs and outputs use the ABI's array-of-structs layout directly: the path is integer-multiply
 // bound (<= 880 B of HBM traffic per 6.19 M-MAC32 pairing), so HBM layout is
 // not what limits it.
@@ -14,7 +14,7 @@
 #include <new>
 
 #include "../../include/pairing_b200.h"
-#include "pairing.cuh"
+#include "curve.cuh"
 #include "pair_tower.cuh"
 #include "codec.cuh"
 
@@ -182,61 +182,6 @@ __global__ void __launch_bounds__(128) k_fq12_op(int op, const uint64_t* a, cons
 // ------------------------------------------------------------------------------------------------
 // Pairing kernels
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_coeffs(uint64_t* p, const Coeffs& c) { st_fp2(p, c.c0); st_fp2(p + 12, c.c1); st_fp2(p + 24, c.c2); }
-__device__ __forceinline__ void ld_coeffs(Coeffs& c, const uint64_t* p) { c.c0 = ld_fp2(p); c.c1 = ld_fp2(p + 12); c.c2 = ld_fp2(p + 24); }
-
-// G2Prepared::from_affine, mod.rs:168-358
-__global__ void __launch_bounds__(128) k_g2_prepare(const uint64_t* q, uint64_t* out, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t* qi = q + G2A_W * i;
-  uint64_t* o = out + (size_t)G2P_W * i;
-  if (qi[24] != 0) {   // infinity: empty coefficient list + flag (mod.rs:169-174); zero-fill the slots
-    for (int w = 0; w < G2P_W - 1; w++) o[w] = 0;
-    o[G2P_W - 1] = 1;
-    return;
-  }
-  Fp2 qx = ld_fp2(qi), qy = ld_fp2(qi + 12);
-  Jac<Fp2> r; r.x = qx; r.y = qy; r.z = fp2_one();
-  Coeffs c;
-  int idx = 0;
-#pragma unroll 1
-  for (int b = BLS_LOOP_TOP; b >= 0; b--) {
-    g2_doubling_step(r, c);
-    st_coeffs(o + 36 * idx, c); idx++;
-    if ((BLS_LOOP_BITS >> b) & 1ull) {
-      g2_addition_step(r, qx, qy, c);
-      st_coeffs(o + 36 * idx, c); idx++;
-    }
-  }
-  g2_doubling_step(r, c);
-  st_coeffs(o + 36 * idx, c);
-  o[G2P_W - 1] = 0;
-}
-
-// n independent single-pair Miller loops (+ optional final exponentiation = Engine::pairing)
-#ifndef BLS_MINB
-#define BLS_MINB 2
-#endif
-template <bool FINAL_EXP>
-__global__ void __launch_bounds__(128, BLS_MINB) k_miller(const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t* pi = p + G1A_W * i;
-  const uint64_t* qi = q + G2A_W * i;
-  bool live = pi[12] == 0 && qi[24] == 0;
-  Fp px = ld_fp(pi), py = ld_fp(pi + 6);
-  Fp2 qx = ld_fp2(qi), qy = ld_fp2(qi + 12);
-  Fp12 f;
-  miller_loop_single(f, px, py, qx, qy, live);
-  if (FINAL_EXP) {
-    Fp12 g;
-    final_exponentiation(g, f);   // Miller values of valid points are non-zero (lib.rs:108 unwrap)
-    st_fp12(out + FQ12_W * i, g);
-  } else {
-    st_fp12(out + FQ12_W * i, f);
-  }
-}
 
 // ---- lane-pair kernels (pair_tower.cuh): two adjacent lanes per pairing, lane c owns coefficient c
 // of every Fq2.  Threads past the end of the batch recompute the last element (every lane has to
@@ -283,6 +228,108 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller(con
   }
 }
 
+__device__ __forceinline__ void pcoeffs_set_one_if(bool dead, PCoeffs& c) {
+  const P2 one = p2_one(), zero = p2_zero();
+  c.c0.v = fp_select(dead, zero.v, c.c0.v);
+  c.c1.v = fp_select(dead, zero.v, c.c1.v);
+  c.c2.v = fp_select(dead, one.v, c.c2.v);
+}
+
+// G2Prepared::from_affine (mod.rs:168-358) on lane pairs: lane c writes coefficient c of every Fq2 of the 68 triples
+__device__ __forceinline__ void st_pcoeffs(uint64_t* p, const PCoeffs& c) { st_p2(p, c.c0); st_p2(p + 12, c.c1); st_p2(p + 24, c.c2); }
+__device__ __forceinline__ void ld_pcoeffs(PCoeffs& c, const uint64_t* p) { c.c0 = ld_p2(p); c.c1 = ld_p2(p + 12); c.c2 = ld_p2(p + 24); }
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_g2_prepare(const uint64_t* q, uint64_t* out, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = t >> 1;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  const uint64_t* qi = q + G2A_W * i;
+  uint64_t* o = out + (size_t)G2P_W * i;
+  const bool inf = qi[24] != 0;      // infinity: empty coefficient list + flag (mod.rs:169-174); the slots are zero-filled
+  const P2 qx = ld_p2(qi), qy = ld_p2(qi + 12);
+  PJac r; r.x = qx; r.y = qy; r.z = p2_one();
+  PCoeffs c;
+  const P2 zero = p2_zero();
+  int idx = 0;
+#pragma unroll 1
+  for (int b = BLS_LOOP_TOP; b >= -1; b--) {
+    pg2_doubling_step(r, c);
+    if (inf) { c.c0 = zero; c.c1 = zero; c.c2 = zero; }
+    if (active) st_pcoeffs(o + 36 * idx, c);
+    idx++;
+    if (b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull)) {
+      pg2_addition_step(r, qx, qy, c);
+      if (inf) { c.c0 = zero; c.c1 = zero; c.c2 = zero; }
+      if (active) st_pcoeffs(o + 36 * idx, c);
+      idx++;
+    }
+  }
+  if (active && pair_c() == 0) o[G2P_W - 1] = inf ? 1ull : 0ull;
+}
+
+// the reference's literal miller_loop (mod.rs:40-102) for n independent pairs, coefficients read from memory
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller_prepared(const uint64_t* p, const uint64_t* qp, uint64_t* out, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = t >> 1;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  const uint64_t* pi = p + G1A_W * i;
+  const uint64_t* qi = qp + (size_t)G2P_W * i;
+  const bool live = pi[12] == 0 && qi[G2P_W - 1] == 0;
+  const Fp px = ld_fp(pi), py = ld_fp(pi + 6);
+  P12 f;
+  p12_one(f);
+  PCoeffs c;
+  int idx = 0;
+#pragma unroll 1
+  for (int b = BLS_LOOP_TOP; b >= -1; b--) {
+    ld_pcoeffs(c, qi + 36 * idx); idx++;
+    p_ell(f, c, px, py);
+    if (b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull)) {
+      ld_pcoeffs(c, qi + 36 * idx); idx++;
+      p_ell(f, c, px, py);
+    }
+    if (b >= 0) p12_sqr(f, f);
+  }
+  p12_conjugate(f);
+  if (!live) p12_one(f);
+  if (active) st_p12(out + FQ12_W * i, f);
+}
+
+// ONE miller_loop over n prepared pairs: lane pair t owns pairs t, t+T, ... and one accumulator (see k_pair_multi_miller)
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_multi_miller_prepared(const uint64_t* p, const uint64_t* qp, size_t n, uint64_t* partials) {
+  const size_t T = ((size_t)gridDim.x * blockDim.x) >> 1;
+  const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+  const size_t per = (n + T - 1) / T;
+  P12 f;
+  p12_one(f);
+  PCoeffs c;
+  int idx = 0;
+#pragma unroll 1
+  for (int b = BLS_LOOP_TOP; b >= -1; b--) {
+    const bool bit = b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull);
+#pragma unroll 1
+    for (int rep = 0; rep < (bit ? 2 : 1); rep++) {
+#pragma unroll 1
+      for (size_t j = 0; j < per; j++) {
+        size_t i = t + j * T;
+        const bool in_range = i < n;
+        if (!in_range) i = n - 1;
+        const uint64_t* pi = p + G1A_W * i;
+        const uint64_t* qi = qp + (size_t)G2P_W * i;
+        const bool dead = !in_range || pi[12] != 0 || qi[G2P_W - 1] != 0;
+        ld_pcoeffs(c, qi + 36 * idx);
+        pcoeffs_set_one_if(dead, c);
+        p_ell(f, c, ld_fp(pi), ld_fp(pi + 6));
+      }
+      idx++;
+    }
+    if (b >= 0) p12_sqr(f, f);
+  }
+  p12_conjugate(f);
+  st_p12(partials + FQ12_W * t, f);
+}
+
 __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_final_exp(const uint64_t* in, uint64_t* out, uint8_t* is_some, size_t n) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = t >> 1;
@@ -327,49 +374,6 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_fq12_pow(c
   if (active) st_p12(out + FQ12_W * i, res);
 }
 
-// Miller loop from stored coefficients, the reference's literal miller_loop (mod.rs:40-102), one pair
-__device__ __forceinline__ void miller_loop_prepared_single(Fp12& f, const Fp& px, const Fp& py, const uint64_t* coeffs, bool live) {
-  fp12_one(f);
-  if (!live) return;
-  Coeffs c;
-  int idx = 0;
-#pragma unroll 1
-  for (int b = BLS_LOOP_TOP; b >= 0; b--) {
-    ld_coeffs(c, coeffs + 36 * idx); idx++;
-    ell(f, c, px, py);
-    if ((BLS_LOOP_BITS >> b) & 1ull) {
-      ld_coeffs(c, coeffs + 36 * idx); idx++;
-      ell(f, c, px, py);
-    }
-    fp12_sqr(f, f);
-  }
-  ld_coeffs(c, coeffs + 36 * idx);
-  ell(f, c, px, py);
-  fp12_conjugate(f);
-}
-
-__global__ void __launch_bounds__(128) k_miller_prepared(const uint64_t* p, const uint64_t* qp, uint64_t* out, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t* pi = p + G1A_W * i;
-  const uint64_t* qi = qp + (size_t)G2P_W * i;
-  bool live = pi[12] == 0 && qi[G2P_W - 1] == 0;
-  Fp px = ld_fp(pi), py = ld_fp(pi + 6);
-  Fp12 f;
-  miller_loop_prepared_single(f, px, py, qi, live);
-  st_fp12(out + FQ12_W * i, f);
-}
-
-__global__ void __launch_bounds__(128) k_final_exp(const uint64_t* in, uint64_t* out, uint8_t* is_some, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fp12 f, g;
-  ld_fp12(f, in + FQ12_W * i);
-  bool ok = final_exponentiation(g, f);
-  st_fp12(out + FQ12_W * i, g);
-  if (is_some) is_some[i] = ok;
-}
-
 // Lane-pair form of the multi-pairing Miller loop (the production path of bls_multi_miller_loop*):
 // lane pair t owns pairs t, t+T, ... and ONE accumulator f.  Lane c keeps coefficient c of the running
 // G2 point R_j in the word-major scratch array: word k of pair j's coefficient c at rstate[(c*36+k)*n + j].
@@ -388,13 +392,6 @@ __device__ __forceinline__ void st_pjac_soa(uint32_t* s, size_t n, size_t pair, 
 #pragma unroll
   for (int k = 0; k < 36; k++) b[(size_t)k * n] = w[k];
 }
-__device__ __forceinline__ void pcoeffs_set_one_if(bool dead, PCoeffs& c) {
-  const P2 one = p2_one(), zero = p2_zero();
-  c.c0.v = fp_select(dead, zero.v, c.c0.v);
-  c.c1.v = fp_select(dead, zero.v, c.c1.v);
-  c.c2.v = fp_select(dead, one.v, c.c2.v);
-}
-
 __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_multi_miller(const uint64_t* p, const uint64_t* q, size_t n, uint32_t* rstate, uint64_t* partials) {
   const size_t T = ((size_t)gridDim.x * blockDim.x) >> 1;                       // lane pairs
   const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
@@ -441,33 +438,6 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_multi_mill
   }
   p12_conjugate(f);
   st_p12(partials + FQ12_W * t, f);
-}
-
-__global__ void __launch_bounds__(128) k_multi_miller_prepared(const uint64_t* p, const uint64_t* qp, size_t n, uint64_t* partials) {
-  const size_t T = (size_t)gridDim.x * blockDim.x;
-  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  Fp12 f;
-  fp12_one(f);
-  Coeffs c;
-  int idx = 0;
-#pragma unroll 1
-  for (int b = BLS_LOOP_TOP; b >= -1; b--) {
-    const bool bit = b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull);
-    for (int rep = 0; rep < (bit ? 2 : 1); rep++) {
-#pragma unroll 1
-      for (size_t i = t; i < n; i += T) {
-        const uint64_t* pi = p + G1A_W * i;
-        const uint64_t* qi = qp + (size_t)G2P_W * i;
-        if (pi[12] != 0 || qi[G2P_W - 1] != 0) continue;
-        ld_coeffs(c, qi + 36 * idx);
-        ell(f, c, ld_fp(pi), ld_fp(pi + 6));
-      }
-      idx++;
-    }
-    if (b >= 0) fp12_sqr(f, f);
-  }
-  fp12_conjugate(f);
-  st_fp12(partials + FQ12_W * t, f);
 }
 
 // Product of `count` Fq12 values: each of T threads multiplies a strided subset of <= 8 factors; the
@@ -909,7 +879,7 @@ int bls_g2_prepare_dev(bls_ctx* ctx, const bls_g2_affine* q, bls_g2_prepared* ou
   if (!ctx || (n && (!q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   CK(cudaSetDevice(ctx->device));
-  k_g2_prepare<<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)q, (uint64_t*)out, n);
+  k_pair_g2_prepare<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
 }
@@ -925,7 +895,7 @@ int bls_miller_loop_prepared_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls
   if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   CK(cudaSetDevice(ctx->device));
-  k_miller_prepared<<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  k_pair_miller_prepared<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
 }
@@ -955,13 +925,6 @@ int bls_fq12_pow_dev(bls_ctx* ctx, const bls_fq12* a, const bls_fr_repr* k, bls_
   return BLS_OK;
 }
 
-// threads (= partial products) of the thread-per-element multi-Miller kernel over prepared coefficients
-static size_t mm_threads_prepared(const bls_ctx* ctx, size_t n) {
-  size_t full = (size_t)ctx->sm_count * 2 * TPB;
-  size_t t = n < full ? n : full;
-  t = (t + TPB - 1) / TPB * TPB;
-  return t ? t : TPB;
-}
 // lane pairs (= partial products) used by the multi-Miller kernel for n pairs: enough pairs per lane pair to
 // amortise the shared squarings, never more lane pairs than pairs; a multiple of the 64 lane pairs of a block
 static size_t mm_threads(const bls_ctx* ctx, size_t n) {
@@ -1201,11 +1164,11 @@ int bls_multi_miller_loop_prepared(bls_ctx* ctx, const bls_g1_affine* p, const b
   CK(cudaSetDevice(ctx->device));
   H2D(dp, p, n * sizeof(*p));
   H2D(dq, q, n * sizeof(*q));
-  size_t T = mm_threads_prepared(ctx, n);
+  size_t T = mm_threads(ctx, n);
   DALLOC(dpart, T * sizeof(bls_fq12));
   DALLOC(dscr, bls_fq12_product_scratch_bytes(ctx, T));
   DALLOC(dout, sizeof(*out1));
-  k_multi_miller_prepared<<<(unsigned)(T / TPB), TPB, 0, ctx->stream>>>((const uint64_t*)dp.p, (const uint64_t*)dq.p, n, (uint64_t*)dpart.p);
+  k_pair_multi_miller_prepared<<<(unsigned)(2 * T / BLS_PAIR_TPB), BLS_PAIR_TPB, 0, ctx->stream>>>((const uint64_t*)dp.p, (const uint64_t*)dq.p, n, (uint64_t*)dpart.p);
   LAUNCH_CHECK();
   TRY(product_passes(ctx, (const uint64_t*)dpart.p, T, (bls_fq12*)dout.p, (uint64_t*)dscr.p, ctx->stream));
   D2H(out1, dout, sizeof(*out1));

@@ -300,10 +300,9 @@ __device__ __forceinline__ void p_ell(P12& f, const PCoeffs& c, const Fp& px, co
   p12_mul_by_014(f, c.c2, c1, c0);
 }
 
-#ifndef BLS_LOOP_BITS
+// The loop schedule: bits of BLS_X >> 1 = 0x6900800000008000 below the leading one, MSB first (mod.rs:72-78)
 #define BLS_LOOP_BITS (BLS_X_ABS >> 1)
-#define BLS_LOOP_TOP 61
-#endif
+#define BLS_LOOP_TOP 61   /* bit 62 is the leading one */
 
 // mod.rs:40-102 for one pair, G2 steps on the fly
 // (no early exit for pairs with an infinity member: every lane must reach every shuffle; the
@@ -327,7 +326,10 @@ __device__ __forceinline__ void p_miller_loop_single(P12& f, const Fp& px, const
   p12_conjugate(f);
 }
 
-// exp_by_x, mod.rs:116-121 (see fp12_exp_by_x in pairing.cuh for the two value-preserving shortcuts)
+// exp_by_x (mod.rs:116-121): Field::pow(&[x]) (lib.rs:306-324) followed by a conjugation.  Two value-preserving
+// shortcuts (SURVEY.md 8c "latitude"): the leading `one * self` product of pow is a copy, and -- the operand being
+// in the cyclotomic subgroup (exp_by_x is only called after the easy part) -- every squaring is a Granger-Scott
+// cyclotomic squaring.
 __device__ __noinline__ void p12_exp_by_x(P12& out, const P12& a, uint64_t x) {
   P12 res = a;
   const int top = 63 - __clzll((long long)x);
