@@ -73,11 +73,12 @@ template <class F> __device__ __noinline__ bool pt_add_core(Jac<F>& s, const Jac
   F u2 = f_mul(o.x, z1z1);
   F s1 = f_mul(f_mul(s.y, o.z), z2z2);
   F s2 = f_mul(f_mul(o.y, s.z), z1z1);
-  if (f_eq(u1, u2) && f_eq(s1, s2)) return true;
   F h = f_sub(u2, u1);
+  F sd = f_sub(s2, s1);
+  if (f_is_zero(h) && f_is_zero(sd)) return true;      // u1 == u2 && s1 == s2: the caller doubles (ec.rs:394-396)
   F i = f_sqr(f_dbl(h));
   F j = f_mul(h, i);
-  F r = f_dbl(f_sub(s2, s1));
+  F r = f_dbl(sd);
   F v = f_mul(u1, i);
   s.x = f_sub(f_sub(f_sub(f_sqr(r), j), v), v);
   s.y = f_sub(f_mul(f_sub(v, s.x), r), f_dbl(f_mul(s1, j)));
@@ -94,12 +95,13 @@ template <class F> __device__ __noinline__ bool pt_add_mixed_core(Jac<F>& s, con
   F z1z1 = f_sqr(s.z);
   F u2 = f_mul(o.x, z1z1);
   F s2 = f_mul(f_mul(o.y, s.z), z1z1);
-  if (f_eq(s.x, u2) && f_eq(s.y, s2)) return true;
   F h = f_sub(u2, s.x);
+  F sd = f_sub(s2, s.y);
+  if (f_is_zero(h) && f_is_zero(sd)) return true;      // same point: the caller doubles (ec.rs:471-473)
   F hh = f_sqr(h);
   F i = f_dbl(f_dbl(hh));
   F j = f_mul(h, i);
-  F r = f_dbl(f_sub(s2, s.y));
+  F r = f_dbl(sd);
   F v = f_mul(s.x, i);
   F x3 = f_sub(f_sub(f_sub(f_sqr(r), j), v), v);
   F y3 = f_sub(f_mul(f_sub(v, x3), r), f_dbl(f_mul(j, s.y)));
