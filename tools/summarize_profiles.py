@@ -5,7 +5,7 @@ import collections, csv, io, re, subprocess, sys
 launch_csv, rep, tag = sys.argv[1:4]
 out = []
 # ---- launch list: per-kernel share of the benchmark command
-rows = [r for r in csv.reader(open(launch_csv)) if len(r) > 10]
+rows = [r for r in csv.reader(open(launch_csv)) if len(r) > 10] if launch_csv != "-" else [["Kernel Name", "Metric Name", "Metric Value"]]
 hdr = rows[0]
 t = collections.defaultdict(lambda: [0, 0.0])
 for r in rows[1:]:
@@ -15,7 +15,7 @@ for r in rows[1:]:
     k = re.sub(r"\(.*", "", d["Kernel Name"])
     t[k][0] += 1
     t[k][1] += float(d["Metric Value"]) / 1e6
-tot = sum(v[1] for v in t.values())
+tot = sum(v[1] for v in t.values()) or 1.0
 out.append("## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`), %s" % launch_csv)
 out.append("")
 out.append("| kernel | launches | total ms | share |")
@@ -37,7 +37,7 @@ keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_elapsed", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
         "smsp__warps_eligible.avg.per_cycle_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
-        "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "sass__inst_executed_local_loads", "sass__inst_executed_local_stores",
         "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct", "l1tex__t_sector_pipe_lsu_mem_local_op_st_hit_rate.pct",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
