@@ -143,3 +143,32 @@ def test_g2_wnaf_and_prepare_sample(eng, data):
     # Miller loop from the stored coefficients == Miller loop with the steps on the fly
     p = pa[:n].contiguous()
     assert torch.equal(eng.miller_loop_prepared_batch(p, prep), eng.miller_loop_batch(p, eng.jacobian_to_affine_rows(wn, 12)))
+
+
+def test_fixed_base_and_gt_pow_device_paths(eng, data):
+    """Wnaf::base(g, n).scalar(s) for 2^18 scalars against ONE shared table (window 14 for G1 at this n) == the per-point
+    wNAF after normalisation; e(P, Q)^k device path == host path; both sampled against the oracle."""
+    pa, qa, g1_jac, ks = data
+    from pairing_b200 import engine
+    n = N_WNAF
+    w = engine.G1.recommended_wnaf_for_num_scalars(n)
+    assert w == 16                                                          # n > 62569 (ec.rs:907-921)
+    base = g1_jac[7:8].contiguous()
+    three = torch.zeros((1, 4), dtype=torch.int64, device=eng.device); three[0, 0] = 3
+    base = eng.g1_wnaf_mul(base, three, 2)                                   # non-normalised base
+    table = eng.wnaf_table(base, w)
+    fixed = eng.wnaf_fixed_base(table, w, ks[:n].contiguous())
+    idx = np.arange(0, n, n // 32)
+    want = o.g1_op("wnaf", np.repeat(_np(base), len(idx), 0), k=_np(ks[:n])[idx], window=w, threads=TH)
+    assert np.array_equal(_np(fixed)[idx], want)
+    per_point = eng.g1_wnaf_mul(base.repeat(n, 1).contiguous(), ks[:n].contiguous())       # window 4 per scalar
+    assert not torch.equal(fixed, per_point)                                 # different Jacobian representatives ...
+    assert torch.equal(eng.g1_batch_normalization_(fixed.clone()), eng.g1_batch_normalization_(per_point))   # ... of the same points
+    m_ = 4096
+    gt = eng.pairing(pa[:m_].contiguous(), qa[:m_].contiguous())
+    pw = eng.fq12_pow(gt, ks[:m_].contiguous())
+    assert np.array_equal(_np(pw)[:64], eng.ctx.fq12_pow(_np(gt)[:64], _np(ks[:m_])[:64]))
+    # e([k]P, Q) == e(P, Q)^k on the whole slice
+    pj = g1_jac[:m_].contiguous()
+    kp = eng.g1_batch_normalization_(eng.g1_wnaf_mul(pj, ks[:m_].contiguous()))
+    assert torch.equal(eng.pairing(eng.jacobian_to_affine_rows(kp, 6), qa[:m_].contiguous()), pw)
