@@ -365,6 +365,25 @@ def run_ours(args):
                                                  config="configs[4]: 2^%d G2 points per GPU: wNAF w=4 + batch_normalization + G2Prepared (19 592 B per point)" % args.g2_log2)
         del prep, aff2
 
+        # rows of SURVEY 8(f) built this round, at moderate sizes (one warm-up, one timed pass)
+        nf = 1 << 20
+        wfix = 16                                                   # recommended_wnaf_for_num_scalars(2^20), ec.rs:907-921
+        fb = g1_jac[5:6].contiguous()
+        ms_tab, table = timed(lambda: eng.wnaf_table(fb, wfix))
+        kf = tile(g1_scalars, nf)
+        fout = torch.empty((nf, 18), dtype=torch.int64, device=eng.device)
+        eng.wnaf_fixed_base(table, wfix, kf[:4096].contiguous())
+        ms_fix, _ = timed(lambda: eng.wnaf_fixed_base(table, wfix, kf, out=fout))
+        secondary["g1_wnaf_fixed_base"] = entry(nf, ms_fix, (254 * 7 + 14 * 16) * 300, unit="scalar-muls/s", window=wfix, ms_table=ms_tab,
+                                               config="SURVEY 8f-1: Wnaf::base(g, 2^20).scalar(s): one 2^15-entry table, 2^20 scalars per GPU")
+        del kf, fout, table
+        npow = 1 << 14
+        gt = out[:npow].contiguous()
+        eng.fq12_pow(gt[:256].contiguous(), g1_scalars[:256].contiguous())
+        ms_pow, _ = timed(lambda: eng.fq12_pow(gt, g1_scalars[:npow].contiguous()))
+        secondary["gt_pow"] = entry(npow, ms_pow, (254 * 36 + 127 * 54) * 300, unit="powers/s",
+                                    config="SURVEY 8f-4: Fq12::pow(FrRepr) for 2^14 GT elements per GPU")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

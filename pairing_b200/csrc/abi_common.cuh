@@ -1,0 +1,94 @@
+// abi_common.cuh -- shared by the two translation units of the library (kernels_pair.cu: the lane-pair pairing
+// engine; kernels.cu: curve, field-op, codec and measurement kernels + the host-buffer entry points).
+// The pairing engine is compiled on its own so that ptxas' register allocation of the routines it shares with
+// nothing else (fp_mul2, p6_mul, ...) cannot be perturbed by unrelated kernels: a two-line change in curve.cuh was
+// measured to slow the fused pairing kernel by 4 % when everything lived in one module.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/pairing_b200.h"
+#include "tower.cuh"
+
+using namespace bls;
+
+// ------------------------------------------------------------------------------------------------
+// ABI <-> register conversions.  ABI structs are arrays of u64 (8-byte aligned).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fp ld_fp(const uint64_t* p) {
+  Fp r;
+  const uint2* q = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+  for (int i = 0; i < 6; i++) { uint2 t = q[i]; r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
+  return r;
+}
+// every value that leaves through the ABI is the canonical representative (< q), as in the reference
+__device__ __forceinline__ void st_fp(uint64_t* p, const Fp& x) {
+  const Fp a = fp_canon(x);
+  uint2* q = reinterpret_cast<uint2*>(p);
+#pragma unroll
+  for (int i = 0; i < 6; i++) q[i] = make_uint2(a.v[2 * i], a.v[2 * i + 1]);
+}
+__device__ __forceinline__ Fp2 ld_fp2(const uint64_t* p) { return Fp2{ld_fp(p), ld_fp(p + 6)}; }
+__device__ __forceinline__ void st_fp2(uint64_t* p, const Fp2& a) { st_fp(p, a.c0); st_fp(p + 6, a.c1); }
+__device__ __forceinline__ void ld_fp6(Fp6& r, const uint64_t* p) { r.c0 = ld_fp2(p); r.c1 = ld_fp2(p + 12); r.c2 = ld_fp2(p + 24); }
+__device__ __forceinline__ void st_fp6(uint64_t* p, const Fp6& a) { st_fp2(p, a.c0); st_fp2(p + 12, a.c1); st_fp2(p + 24, a.c2); }
+__device__ __forceinline__ void ld_fp12(Fp12& r, const uint64_t* p) { ld_fp6(r.c0, p); ld_fp6(r.c1, p + 36); }
+__device__ __forceinline__ void st_fp12(uint64_t* p, const Fp12& a) { st_fp6(p, a.c0); st_fp6(p + 36, a.c1); }
+
+__device__ __forceinline__ Scalar ld_scalar(const uint64_t* p) {
+  Scalar s;
+  const uint2* q = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; i++) { uint2 t = q[i]; s.v[2 * i] = t.x; s.v[2 * i + 1] = t.y; }
+  return s;
+}
+
+#define G1A_W 13
+#define G1_W 18
+#define G2A_W 25
+#define G2_W 36
+#define FQ12_W 72
+#define G2P_W (68 * 36 + 1)
+
+// ------------------------------------------------------------------------------------------------
+// Host side: context
+// ------------------------------------------------------------------------------------------------
+struct bls_ctx {
+  int device;
+  int sm_count;
+  cudaStream_t stream;
+  uint64_t launches;
+  char last_error[256];
+};
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      snprintf(ctx->last_error, sizeof(ctx->last_error), "%s: %s", #call, cudaGetErrorString(e_)); \
+      return e_ == cudaErrorMemoryAllocation ? BLS_ERR_OUT_OF_MEMORY : BLS_ERR_CUDA;  \
+    }                                                                                 \
+  } while (0)
+
+static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+static const int TPB = 128;
+
+static inline cudaStream_t pick(bls_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
+
+#define LAUNCH_CHECK()                                  \
+  do {                                                  \
+    ctx->launches++;                                    \
+    CK(cudaGetLastError());                             \
+  } while (0)
+
+#define BLS_INTERNAL __attribute__((visibility("hidden")))
+// cross-unit helpers (not part of the ABI)
+extern "C" {
+BLS_INTERNAL int bls_internal_product_passes(bls_ctx* ctx, const uint64_t* in, size_t count, bls_fq12* out1, uint64_t* scratch, cudaStream_t s);
+BLS_INTERNAL size_t bls_internal_mm_lane_pairs(const bls_ctx* ctx, size_t n);
+BLS_INTERNAL int bls_internal_multi_miller_prepared(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* qp, size_t n, bls_fq12* partials, cudaStream_t s);
+}

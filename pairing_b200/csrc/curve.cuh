@@ -128,8 +128,7 @@ template <class F> __device__ __noinline__ void pt_into_affine(Aff<F>& out, cons
   out.y = f_mul(p.y, f_mul(zp, zinv));
 }
 
-// ---- scalars (FrRepr, fr.rs:57-244): canonical 256-bit integers, 8 x u32 here ----
-struct Scalar { uint32_t v[8]; };
+// ---- scalars (FrRepr, fr.rs:57-244): canonical 256-bit integers, 8 x u32 (struct Scalar, fp.cuh) ----
 
 __device__ __forceinline__ int scalar_num_bits(const Scalar& k) {   // fr.rs:213-225
   for (int i = 7; i >= 0; i--)

@@ -421,8 +421,11 @@ __device__ __forceinline__ Fp fp_mul2_inline(const Fp& x, const Fp& bx, const Fp
   return fp_merge(o, e);
 }
 
-__device__ __noinline__ Fp fp_mul(Fp a, Fp b) { return fp_mul_inline(a, b); }
-__device__ __noinline__ Fp fp_mul2(Fp x, Fp bx, Fp y, Fp by) { return fp_mul2_inline(x, bx, y, by); }
+static __device__ __noinline__ Fp fp_mul(Fp a, Fp b) { return fp_mul_inline(a, b); }
+static __device__ __noinline__ Fp fp_mul2(Fp x, Fp bx, Fp y, Fp by) { return fp_mul2_inline(x, bx, y, by); }
 __device__ __forceinline__ Fp fp_sqr(const Fp& a) { return fp_mul(a, a); }   // one copy of the product code (instruction-cache footprint)
+
+// FrRepr (fr.rs:57-58): a canonical 256-bit integer as 8 x u32 -- scalars and GT exponents
+struct Scalar { uint32_t v[8]; };
 
 }  // namespace bls

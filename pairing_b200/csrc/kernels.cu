@@ -1,48 +1,15 @@
-// kernels.cu -- CUDA kernels (sm_100a) and the C ABI of include/pairing_b200.h.
-//
-// Mapping: the pairing engine (Miller loops, final exponentiation, G2Prepared, GT powers) runs on LANE PAIRS
-// (pair_tower.cuh: two lanes per Fq2-valued object); the curve kernels (group law, wNAF, normalisation,
-// encodings) and the field-op test kernels run one thread per element (tower.cuh, curve.cuh).
+// kernels.cu -- curve, field-op, codec and measurement kernels (one thread per element: tower.cuh, curve.cuh,
+// codec.cuh), the context, and every host-buffer entry point of include/pairing_b200.h.  The pairing engine
+// (Miller loops, final exponentiation, G2Prepared, GT powers) runs on LANE PAIRS and lives in kernels_pair.cu.
 // Inputs and outputs use the ABI's array-of-structs layout directly: the path is integer-multiply
 // bound (<= 880 B of HBM traffic per 6.19 M-MAC32 pairing), so HBM layout is
 // not what limits it.
-#include <cuda_runtime.h>
-#include <stdint.h>
-#include <stdio.h>
-#include <string.h>
+#include "abi_common.cuh"
 
 #include <new>
 
-#include "../../include/pairing_b200.h"
 #include "curve.cuh"
-#include "pair_tower.cuh"
 #include "codec.cuh"
-
-using namespace bls;
-
-// ------------------------------------------------------------------------------------------------
-// ABI <-> register conversions.  ABI structs are arrays of u64 (8-byte aligned).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ Fp ld_fp(const uint64_t* p) {
-  Fp r;
-  const uint2* q = reinterpret_cast<const uint2*>(p);
-#pragma unroll
-  for (int i = 0; i < 6; i++) { uint2 t = q[i]; r.v[2 * i] = t.x; r.v[2 * i + 1] = t.y; }
-  return r;
-}
-// every value that leaves through the ABI is the canonical representative (< q), as in the reference
-__device__ __forceinline__ void st_fp(uint64_t* p, const Fp& x) {
-  const Fp a = fp_canon(x);
-  uint2* q = reinterpret_cast<uint2*>(p);
-#pragma unroll
-  for (int i = 0; i < 6; i++) q[i] = make_uint2(a.v[2 * i], a.v[2 * i + 1]);
-}
-__device__ __forceinline__ Fp2 ld_fp2(const uint64_t* p) { return Fp2{ld_fp(p), ld_fp(p + 6)}; }
-__device__ __forceinline__ void st_fp2(uint64_t* p, const Fp2& a) { st_fp(p, a.c0); st_fp(p + 6, a.c1); }
-__device__ __forceinline__ void ld_fp6(Fp6& r, const uint64_t* p) { r.c0 = ld_fp2(p); r.c1 = ld_fp2(p + 12); r.c2 = ld_fp2(p + 24); }
-__device__ __forceinline__ void st_fp6(uint64_t* p, const Fp6& a) { st_fp2(p, a.c0); st_fp2(p + 12, a.c1); st_fp2(p + 24, a.c2); }
-__device__ __forceinline__ void ld_fp12(Fp12& r, const uint64_t* p) { ld_fp6(r.c0, p); ld_fp6(r.c1, p + 36); }
-__device__ __forceinline__ void st_fp12(uint64_t* p, const Fp12& a) { st_fp6(p, a.c0); st_fp6(p + 36, a.c1); }
 
 __device__ __forceinline__ void ld_F(Fp& r, const uint64_t* p) { r = ld_fp(p); }
 __device__ __forceinline__ void ld_F(Fp2& r, const uint64_t* p) { r = ld_fp2(p); }
@@ -64,20 +31,6 @@ template <class F> __device__ __forceinline__ void ld_aff(Aff<F>& r, const uint6
 template <class F> __device__ __forceinline__ void st_aff(uint64_t* p, const Aff<F>& a) {
   st_F(p, a.x); st_F(p + FW<F>::W, a.y); p[2 * FW<F>::W] = a.inf ? 1ull : 0ull;
 }
-__device__ __forceinline__ Scalar ld_scalar(const uint64_t* p) {
-  Scalar s;
-  const uint2* q = reinterpret_cast<const uint2*>(p);
-#pragma unroll
-  for (int i = 0; i < 4; i++) { uint2 t = q[i]; s.v[2 * i] = t.x; s.v[2 * i + 1] = t.y; }
-  return s;
-}
-
-#define G1A_W 13
-#define G1_W 18
-#define G2A_W 25
-#define G2_W 36
-#define FQ12_W 72
-#define G2P_W (68 * 36 + 1)
 
 // ------------------------------------------------------------------------------------------------
 // Field-op kernels (tower parity tests; `Field` trait methods, src/lib.rs:267-325)
@@ -182,263 +135,6 @@ __global__ void __launch_bounds__(128) k_fq12_op(int op, const uint64_t* a, cons
 // ------------------------------------------------------------------------------------------------
 // Pairing kernels
 // ------------------------------------------------------------------------------------------------
-
-// ---- lane-pair kernels (pair_tower.cuh): two adjacent lanes per pairing, lane c owns coefficient c
-// of every Fq2.  Threads past the end of the batch recompute the last element (every lane has to
-// reach every shuffle) and skip the store.
-__device__ __forceinline__ P2 ld_p2(const uint64_t* p) { return P2{ld_fp(p + 6 * pair_c())}; }
-__device__ __forceinline__ void st_p2(uint64_t* p, const P2& a) { st_fp(p + 6 * pair_c(), a.v); }
-__device__ __forceinline__ void ld_p12(P12& r, const uint64_t* p) {
-  r.c0.c0 = ld_p2(p); r.c0.c1 = ld_p2(p + 12); r.c0.c2 = ld_p2(p + 24);
-  r.c1.c0 = ld_p2(p + 36); r.c1.c1 = ld_p2(p + 48); r.c1.c2 = ld_p2(p + 60);
-}
-__device__ __forceinline__ void st_p12(uint64_t* p, const P12& a) {
-  st_p2(p, a.c0.c0); st_p2(p + 12, a.c0.c1); st_p2(p + 24, a.c0.c2);
-  st_p2(p + 36, a.c1.c0); st_p2(p + 48, a.c1.c1); st_p2(p + 60, a.c1.c2);
-}
-
-// launch shape of the lane-pair kernels: BLS_PAIR_TPB threads per block, BLS_PAIR_MINB blocks per SM
-// (registers per thread <= 65536 / (TPB * MINB)).  Small blocks keep the tail of a 2^16 batch short.
-#ifndef BLS_PAIR_TPB
-#define BLS_PAIR_TPB 128
-#endif
-#ifndef BLS_PAIR_MINB
-#define BLS_PAIR_MINB 2
-#endif
-template <bool FINAL_EXP>
-__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller(const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t i = t >> 1;
-  const bool active = i < n;
-  if (!active) i = n - 1;
-  const uint64_t* pi = p + G1A_W * i;
-  const uint64_t* qi = q + G2A_W * i;
-  const bool live = pi[12] == 0 && qi[24] == 0;
-  Fp px = ld_fp(pi), py = ld_fp(pi + 6);
-  P2 qx = ld_p2(qi), qy = ld_p2(qi + 12);
-  P12 f;
-  p_miller_loop_single(f, px, py, qx, qy);
-  if (!live) p12_one(f);                       // mod.rs:49-54: skipped pair, f stays one
-  if (FINAL_EXP) {
-    P12 g;
-    p_final_exponentiation(g, f);
-    if (active) st_p12(out + FQ12_W * i, g);
-  } else {
-    if (active) st_p12(out + FQ12_W * i, f);
-  }
-}
-
-__device__ __forceinline__ void pcoeffs_set_one_if(bool dead, PCoeffs& c) {
-  const P2 one = p2_one(), zero = p2_zero();
-  c.c0.v = fp_select(dead, zero.v, c.c0.v);
-  c.c1.v = fp_select(dead, zero.v, c.c1.v);
-  c.c2.v = fp_select(dead, one.v, c.c2.v);
-}
-
-// G2Prepared::from_affine (mod.rs:168-358) on lane pairs: lane c writes coefficient c of every Fq2 of the 68 triples
-__device__ __forceinline__ void st_pcoeffs(uint64_t* p, const PCoeffs& c) { st_p2(p, c.c0); st_p2(p + 12, c.c1); st_p2(p + 24, c.c2); }
-__device__ __forceinline__ void ld_pcoeffs(PCoeffs& c, const uint64_t* p) { c.c0 = ld_p2(p); c.c1 = ld_p2(p + 12); c.c2 = ld_p2(p + 24); }
-__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_g2_prepare(const uint64_t* q, uint64_t* out, size_t n) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t i = t >> 1;
-  const bool active = i < n;
-  if (!active) i = n - 1;
-  const uint64_t* qi = q + G2A_W * i;
-  uint64_t* o = out + (size_t)G2P_W * i;
-  const bool inf = qi[24] != 0;      // infinity: empty coefficient list + flag (mod.rs:169-174); the slots are zero-filled
-  const P2 qx = ld_p2(qi), qy = ld_p2(qi + 12);
-  PJac r; r.x = qx; r.y = qy; r.z = p2_one();
-  PCoeffs c;
-  const P2 zero = p2_zero();
-  int idx = 0;
-#pragma unroll 1
-  for (int b = BLS_LOOP_TOP; b >= -1; b--) {
-    pg2_doubling_step(r, c);
-    if (inf) { c.c0 = zero; c.c1 = zero; c.c2 = zero; }
-    if (active) st_pcoeffs(o + 36 * idx, c);
-    idx++;
-    if (b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull)) {
-      pg2_addition_step(r, qx, qy, c);
-      if (inf) { c.c0 = zero; c.c1 = zero; c.c2 = zero; }
-      if (active) st_pcoeffs(o + 36 * idx, c);
-      idx++;
-    }
-  }
-  if (active && pair_c() == 0) o[G2P_W - 1] = inf ? 1ull : 0ull;
-}
-
-// the reference's literal miller_loop (mod.rs:40-102) for n independent pairs, coefficients read from memory
-__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller_prepared(const uint64_t* p, const uint64_t* qp, uint64_t* out, size_t n) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t i = t >> 1;
-  const bool active = i < n;
-  if (!active) i = n - 1;
-  const uint64_t* pi = p + G1A_W * i;
-  const uint64_t* qi = qp + (size_t)G2P_W * i;
-  const bool live = pi[12] == 0 && qi[G2P_W - 1] == 0;
-  const Fp px = ld_fp(pi), py = ld_fp(pi + 6);
-  P12 f;
-  p12_one(f);
-  PCoeffs c;
-  int idx = 0;
-#pragma unroll 1
-  for (int b = BLS_LOOP_TOP; b >= -1; b--) {
-    ld_pcoeffs(c, qi + 36 * idx); idx++;
-    p_ell(f, c, px, py);
-    if (b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull)) {
-      ld_pcoeffs(c, qi + 36 * idx); idx++;
-      p_ell(f, c, px, py);
-    }
-    if (b >= 0) p12_sqr(f, f);
-  }
-  p12_conjugate(f);
-  if (!live) p12_one(f);
-  if (active) st_p12(out + FQ12_W * i, f);
-}
-
-// ONE miller_loop over n prepared pairs: lane pair t owns pairs t, t+T, ... and one accumulator (see k_pair_multi_miller)
-__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_multi_miller_prepared(const uint64_t* p, const uint64_t* qp, size_t n, uint64_t* partials) {
-  const size_t T = ((size_t)gridDim.x * blockDim.x) >> 1;
-  const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-  const size_t per = (n + T - 1) / T;
-  P12 f;
-  p12_one(f);
-  PCoeffs c;
-  int idx = 0;
-#pragma unroll 1
-  for (int b = BLS_LOOP_TOP; b >= -1; b--) {
-    const bool bit = b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull);
-#pragma unroll 1
-    for (int rep = 0; rep < (bit ? 2 : 1); rep++) {
-#pragma unroll 1
-      for (size_t j = 0; j < per; j++) {
-        size_t i = t + j * T;
-        const bool in_range = i < n;
-        if (!in_range) i = n - 1;
-        const uint64_t* pi = p + G1A_W * i;
-        const uint64_t* qi = qp + (size_t)G2P_W * i;
-        const bool dead = !in_range || pi[12] != 0 || qi[G2P_W - 1] != 0;
-        ld_pcoeffs(c, qi + 36 * idx);
-        pcoeffs_set_one_if(dead, c);
-        p_ell(f, c, ld_fp(pi), ld_fp(pi + 6));
-      }
-      idx++;
-    }
-    if (b >= 0) p12_sqr(f, f);
-  }
-  p12_conjugate(f);
-  st_p12(partials + FQ12_W * t, f);
-}
-
-__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_final_exp(const uint64_t* in, uint64_t* out, uint8_t* is_some, size_t n) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t i = t >> 1;
-  const bool active = i < n;
-  if (!active) i = n - 1;
-  P12 f, g;
-  ld_p12(f, in + FQ12_W * i);
-  bool ok = p_final_exponentiation(g, f);
-  if (active) {
-    st_p12(out + FQ12_W * i, g);
-    if (is_some && pair_c() == 0) is_some[i] = ok;
-  }
-}
-
-// Field::pow on Fq12 with an FrRepr exponent (lib.rs:306-324; GT exponentiation, tests/engine.rs:121):
-// MSB-first square-and-multiply.  The exponent differs per lane pair, so the loop is branch-free over all
-// 256 bits (every lane has to reach every shuffle): squarings and products are computed for the whole warp
-// and committed per lane pair.  Generic squaring (the input need not be in the cyclotomic subgroup).
-__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_fq12_pow(const uint64_t* in, const uint64_t* k, uint64_t* out, size_t n) {
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t i = t >> 1;
-  const bool active = i < n;
-  if (!active) i = n - 1;
-  P12 a, res, tmp;
-  ld_p12(a, in + FQ12_W * i);
-  Scalar s = ld_scalar(k + 4 * i);
-  p12_one(res);
-  bool found = false;
-#pragma unroll 1
-  for (int b = 255; b >= 0; b--) {
-    const bool bit = (s.v[b >> 5] >> (b & 31)) & 1u;
-    if (__any_sync(0xffffffffu, found)) {
-      p12_sqr(tmp, res);
-      p12_select(res, found, tmp, res);
-    }
-    found |= bit;
-    if (__any_sync(0xffffffffu, bit)) {
-      p12_mul(tmp, res, a);
-      p12_select(res, bit, tmp, res);
-    }
-  }
-  if (active) st_p12(out + FQ12_W * i, res);
-}
-
-// Lane-pair form of the multi-pairing Miller loop (the production path of bls_multi_miller_loop*):
-// lane pair t owns pairs t, t+T, ... and ONE accumulator f.  Lane c keeps coefficient c of the running
-// G2 point R_j in the word-major scratch array: word k of pair j's coefficient c at rstate[(c*36+k)*n + j].
-// Every lane has to reach every shuffle, so there is no `continue`: a pair with an infinity member
-// (mod.rs:49-54) or past the end of the batch multiplies f by the sparse element (1, 0, 0) = one instead,
-// which leaves the canonical value of f unchanged.
-__device__ __forceinline__ void ld_pjac_soa(PJac& r, const uint32_t* s, size_t n, size_t pair) {
-  uint32_t* w = reinterpret_cast<uint32_t*>(&r);
-  const uint32_t* b = s + (size_t)pair_c() * 36 * n + pair;
-#pragma unroll
-  for (int k = 0; k < 36; k++) w[k] = b[(size_t)k * n];
-}
-__device__ __forceinline__ void st_pjac_soa(uint32_t* s, size_t n, size_t pair, const PJac& r) {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
-  uint32_t* b = s + (size_t)pair_c() * 36 * n + pair;
-#pragma unroll
-  for (int k = 0; k < 36; k++) b[(size_t)k * n] = w[k];
-}
-__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_multi_miller(const uint64_t* p, const uint64_t* q, size_t n, uint32_t* rstate, uint64_t* partials) {
-  const size_t T = ((size_t)gridDim.x * blockDim.x) >> 1;                       // lane pairs
-  const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-  const size_t per = (n + T - 1) / T;                                            // loop trips, uniform over the grid
-  P12 f;
-  p12_one(f);
-  PCoeffs c;
-  PJac r;
-#pragma unroll 1
-  for (int b = BLS_LOOP_TOP; b >= -1; b--) {   // b == -1 is the trailing doubling step (mod.rs:92-94)
-    const bool bit = b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull);
-#pragma unroll 1
-    for (size_t j = 0; j < per; j++) {
-      size_t i = t + j * T;
-      const bool in_range = i < n;
-      if (!in_range) i = n - 1;
-      const uint64_t* pi = p + G1A_W * i;
-      const uint64_t* qi = q + G2A_W * i;
-      const bool dead = !in_range || pi[12] != 0 || qi[24] != 0;
-      if (b == BLS_LOOP_TOP) { r.x = ld_p2(qi); r.y = ld_p2(qi + 12); r.z = p2_one(); }
-      else ld_pjac_soa(r, rstate, n, i);
-      pg2_doubling_step(r, c);
-      pcoeffs_set_one_if(dead, c);
-      p_ell(f, c, ld_fp(pi), ld_fp(pi + 6));
-      if (b >= 0 && in_range) st_pjac_soa(rstate, n, i, r);
-    }
-    if (bit) {
-#pragma unroll 1
-      for (size_t j = 0; j < per; j++) {
-        size_t i = t + j * T;
-        const bool in_range = i < n;
-        if (!in_range) i = n - 1;
-        const uint64_t* pi = p + G1A_W * i;
-        const uint64_t* qi = q + G2A_W * i;
-        const bool dead = !in_range || pi[12] != 0 || qi[24] != 0;
-        ld_pjac_soa(r, rstate, n, i);
-        pg2_addition_step(r, ld_p2(qi), ld_p2(qi + 12), c);
-        pcoeffs_set_one_if(dead, c);
-        p_ell(f, c, ld_fp(pi), ld_fp(pi + 6));
-        if (in_range) st_pjac_soa(rstate, n, i, r);
-      }
-    }
-    if (b >= 0) p12_sqr(f, f);
-  }
-  p12_conjugate(f);
-  st_p12(partials + FQ12_W * t, f);
-}
 
 // Product of `count` Fq12 values: each of T threads multiplies a strided subset of <= 8 factors; the
 // host repeats the pass (count -> ceil(count/8)) until one value is left.
@@ -795,26 +491,6 @@ __global__ void __launch_bounds__(256) k_carry_row_peak(uint32_t seed, int iters
 // ------------------------------------------------------------------------------------------------
 // Host side: context + C ABI
 // ------------------------------------------------------------------------------------------------
-struct bls_ctx {
-  int device;
-  int sm_count;
-  cudaStream_t stream;
-  uint64_t launches;
-  char last_error[256];
-};
-
-#define CK(call)                                                                      \
-  do {                                                                                \
-    cudaError_t e_ = (call);                                                          \
-    if (e_ != cudaSuccess) {                                                          \
-      snprintf(ctx->last_error, sizeof(ctx->last_error), "%s: %s", #call, cudaGetErrorString(e_)); \
-      return e_ == cudaErrorMemoryAllocation ? BLS_ERR_OUT_OF_MEMORY : BLS_ERR_CUDA;  \
-    }                                                                                 \
-  } while (0)
-
-static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
-static const int TPB = 128;
-
 extern "C" {
 
 bls_ctx* bls_ctx_create(int device, int* err) {
@@ -864,89 +540,15 @@ uint64_t bls_ctx_launch_count(const bls_ctx* ctx) { return ctx ? ctx->launches :
 
 }  // extern "C"
 
-static inline cudaStream_t pick(bls_ctx* ctx, void* stream) { return stream ? (cudaStream_t)stream : ctx->stream; }
-
-#define LAUNCH_CHECK()                                  \
-  do {                                                  \
-    ctx->launches++;                                    \
-    CK(cudaGetLastError());                             \
-  } while (0)
-
 // ---- device-pointer entry points --------------------------------------------------------------
 extern "C" {
-
-int bls_g2_prepare_dev(bls_ctx* ctx, const bls_g2_affine* q, bls_g2_prepared* out, size_t n, void* stream) {
-  if (!ctx || (n && (!q || !out))) return BLS_ERR_INVALID_ARGUMENT;
-  if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
-  k_pair_g2_prepare<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)q, (uint64_t*)out, n);
-  LAUNCH_CHECK();
-  return BLS_OK;
-}
-int bls_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream) {
-  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
-  if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
-  k_pair_miller<false><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
-  LAUNCH_CHECK();
-  return BLS_OK;
-}
-int bls_miller_loop_prepared_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q, bls_fq12* out, size_t n, void* stream) {
-  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
-  if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
-  k_pair_miller_prepared<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
-  LAUNCH_CHECK();
-  return BLS_OK;
-}
-int bls_final_exponentiation_dev(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n, void* stream) {
-  if (!ctx || (n && (!in || !out))) return BLS_ERR_INVALID_ARGUMENT;
-  if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
-  k_pair_final_exp<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)in, (uint64_t*)out, is_some, n);
-  LAUNCH_CHECK();
-  return BLS_OK;
-}
-int bls_pairing_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream) {
-  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
-  if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
-  k_pair_miller<true><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
-  LAUNCH_CHECK();
-  return BLS_OK;
-}
-
-int bls_fq12_pow_dev(bls_ctx* ctx, const bls_fq12* a, const bls_fr_repr* k, bls_fq12* out, size_t n, void* stream) {
-  if (!ctx || (n && (!a || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
-  if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
-  k_pair_fq12_pow<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)a, (const uint64_t*)k, (uint64_t*)out, n);
-  LAUNCH_CHECK();
-  return BLS_OK;
-}
-
-// lane pairs (= partial products) used by the multi-Miller kernel for n pairs: enough pairs per lane pair to
-// amortise the shared squarings, never more lane pairs than pairs; a multiple of the 64 lane pairs of a block
-static size_t mm_threads(const bls_ctx* ctx, size_t n) {
-  const size_t per_block = BLS_PAIR_TPB / 2;
-  size_t full = (size_t)ctx->sm_count * BLS_PAIR_MINB * per_block;
-  size_t t = n < full ? n : full;
-  t = (t + per_block - 1) / per_block * per_block;
-  return t ? t : per_block;
-}
 // product tree: a pass over `count` factors uses ceil(count/8) threads
 static size_t prod_threads(size_t count) { return count ? (count + 7) / 8 : 1; }
 size_t bls_fq12_product_scratch_bytes(const bls_ctx* ctx, size_t n) {
   (void)ctx;
   return 2 * prod_threads(n) * sizeof(bls_fq12);
 }
-size_t bls_multi_miller_scratch_bytes(const bls_ctx* ctx, size_t n) {
-  if (!ctx) return 0;
-  size_t T = mm_threads(ctx, n);
-  return n * 72 * sizeof(uint32_t) + T * sizeof(bls_fq12) + bls_fq12_product_scratch_bytes(ctx, T);
-}
-
-static int product_passes(bls_ctx* ctx, const uint64_t* in, size_t count, bls_fq12* out1, uint64_t* scratch, cudaStream_t s) {
+int bls_internal_product_passes(bls_ctx* ctx, const uint64_t* in, size_t count, bls_fq12* out1, uint64_t* scratch, cudaStream_t s) {
   // scratch holds two ping-pong arrays of prod_threads(count) Fq12 each
   const size_t cap = prod_threads(count);
   uint64_t* bufs[2] = {scratch, scratch + cap * FQ12_W};
@@ -973,25 +575,7 @@ int bls_fq12_product_dev(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq12* o
     LAUNCH_CHECK();
     return BLS_OK;
   }
-  return product_passes(ctx, (const uint64_t*)in, n, out1, (uint64_t*)scratch, s);
-}
-
-int bls_multi_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, void* scratch, void* stream) {
-  if (!ctx || !out1 || (n && (!p || !q || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
-  CK(cudaSetDevice(ctx->device));
-  cudaStream_t s = pick(ctx, stream);
-  if (n == 0) {
-    k_fq12_product<<<1, TPB, 0, s>>>(nullptr, 0, (uint64_t*)out1, 1);
-    LAUNCH_CHECK();
-    return BLS_OK;
-  }
-  size_t T = mm_threads(ctx, n);
-  uint32_t* rstate = (uint32_t*)scratch;
-  uint64_t* partials = (uint64_t*)((char*)scratch + n * 72 * sizeof(uint32_t));
-  uint64_t* prod_scratch = partials + T * FQ12_W;
-  k_pair_multi_miller<<<(unsigned)(2 * T / BLS_PAIR_TPB), BLS_PAIR_TPB, 0, s>>>((const uint64_t*)p, (const uint64_t*)q, n, rstate, partials);
-  LAUNCH_CHECK();
-  return product_passes(ctx, partials, T, out1, prod_scratch, s);
+  return bls_internal_product_passes(ctx, (const uint64_t*)in, n, out1, (uint64_t*)scratch, s);
 }
 
 int bls_g1_wnaf_mul_dev(bls_ctx* ctx, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n, int window, void* stream) {
@@ -1164,13 +748,12 @@ int bls_multi_miller_loop_prepared(bls_ctx* ctx, const bls_g1_affine* p, const b
   CK(cudaSetDevice(ctx->device));
   H2D(dp, p, n * sizeof(*p));
   H2D(dq, q, n * sizeof(*q));
-  size_t T = mm_threads(ctx, n);
+  size_t T = bls_internal_mm_lane_pairs(ctx, n);
   DALLOC(dpart, T * sizeof(bls_fq12));
   DALLOC(dscr, bls_fq12_product_scratch_bytes(ctx, T));
   DALLOC(dout, sizeof(*out1));
-  k_pair_multi_miller_prepared<<<(unsigned)(2 * T / BLS_PAIR_TPB), BLS_PAIR_TPB, 0, ctx->stream>>>((const uint64_t*)dp.p, (const uint64_t*)dq.p, n, (uint64_t*)dpart.p);
-  LAUNCH_CHECK();
-  TRY(product_passes(ctx, (const uint64_t*)dpart.p, T, (bls_fq12*)dout.p, (uint64_t*)dscr.p, ctx->stream));
+  TRY(bls_internal_multi_miller_prepared(ctx, (const bls_g1_affine*)dp.p, (const bls_g2_prepared*)dq.p, n, (bls_fq12*)dpart.p, ctx->stream));
+  TRY(bls_internal_product_passes(ctx, (const uint64_t*)dpart.p, T, (bls_fq12*)dout.p, (uint64_t*)dscr.p, ctx->stream));
   D2H(out1, dout, sizeof(*out1));
   SYNC();
   return BLS_OK;

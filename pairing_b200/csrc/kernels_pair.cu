@@ -1,0 +1,355 @@
+// kernels_pair.cu -- the pairing engine on LANE PAIRS (pair_tower.cuh): Miller loops, final exponentiation, the fused
+// pairing kernel, G2Prepared, multi-pairing Miller loop, GT powers, and their device-pointer entry points.
+// Its own translation unit: see abi_common.cuh.
+#include "abi_common.cuh"
+#include "pair_tower.cuh"
+
+// ---- lane-pair kernels (pair_tower.cuh): two adjacent lanes per pairing, lane c owns coefficient c
+// of every Fq2.  Threads past the end of the batch recompute the last element (every lane has to
+// reach every shuffle) and skip the store.
+__device__ __forceinline__ P2 ld_p2(const uint64_t* p) { return P2{ld_fp(p + 6 * pair_c())}; }
+__device__ __forceinline__ void st_p2(uint64_t* p, const P2& a) { st_fp(p + 6 * pair_c(), a.v); }
+__device__ __forceinline__ void ld_p12(P12& r, const uint64_t* p) {
+  r.c0.c0 = ld_p2(p); r.c0.c1 = ld_p2(p + 12); r.c0.c2 = ld_p2(p + 24);
+  r.c1.c0 = ld_p2(p + 36); r.c1.c1 = ld_p2(p + 48); r.c1.c2 = ld_p2(p + 60);
+}
+__device__ __forceinline__ void st_p12(uint64_t* p, const P12& a) {
+  st_p2(p, a.c0.c0); st_p2(p + 12, a.c0.c1); st_p2(p + 24, a.c0.c2);
+  st_p2(p + 36, a.c1.c0); st_p2(p + 48, a.c1.c1); st_p2(p + 60, a.c1.c2);
+}
+
+// launch shape of the lane-pair kernels: BLS_PAIR_TPB threads per block, BLS_PAIR_MINB blocks per SM
+// (registers per thread <= 65536 / (TPB * MINB)).  Small blocks keep the tail of a 2^16 batch short.
+#ifndef BLS_PAIR_TPB
+#define BLS_PAIR_TPB 128
+#endif
+#ifndef BLS_PAIR_MINB
+#define BLS_PAIR_MINB 2
+#endif
+template <bool FINAL_EXP>
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller(const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = t >> 1;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  const uint64_t* pi = p + G1A_W * i;
+  const uint64_t* qi = q + G2A_W * i;
+  const bool live = pi[12] == 0 && qi[24] == 0;
+  Fp px = ld_fp(pi), py = ld_fp(pi + 6);
+  P2 qx = ld_p2(qi), qy = ld_p2(qi + 12);
+  P12 f;
+  p_miller_loop_single(f, px, py, qx, qy);
+  if (!live) p12_one(f);                       // mod.rs:49-54: skipped pair, f stays one
+  if (FINAL_EXP) {
+    P12 g;
+    p_final_exponentiation(g, f);
+    if (active) st_p12(out + FQ12_W * i, g);
+  } else {
+    if (active) st_p12(out + FQ12_W * i, f);
+  }
+}
+
+__device__ __forceinline__ void pcoeffs_set_one_if(bool dead, PCoeffs& c) {
+  const P2 one = p2_one(), zero = p2_zero();
+  c.c0.v = fp_select(dead, zero.v, c.c0.v);
+  c.c1.v = fp_select(dead, zero.v, c.c1.v);
+  c.c2.v = fp_select(dead, one.v, c.c2.v);
+}
+
+// G2Prepared::from_affine (mod.rs:168-358) on lane pairs: lane c writes coefficient c of every Fq2 of the 68 triples
+__device__ __forceinline__ void st_pcoeffs(uint64_t* p, const PCoeffs& c) { st_p2(p, c.c0); st_p2(p + 12, c.c1); st_p2(p + 24, c.c2); }
+__device__ __forceinline__ void ld_pcoeffs(PCoeffs& c, const uint64_t* p) { c.c0 = ld_p2(p); c.c1 = ld_p2(p + 12); c.c2 = ld_p2(p + 24); }
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_g2_prepare(const uint64_t* q, uint64_t* out, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = t >> 1;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  const uint64_t* qi = q + G2A_W * i;
+  uint64_t* o = out + (size_t)G2P_W * i;
+  const bool inf = qi[24] != 0;      // infinity: empty coefficient list + flag (mod.rs:169-174); the slots are zero-filled
+  const P2 qx = ld_p2(qi), qy = ld_p2(qi + 12);
+  PJac r; r.x = qx; r.y = qy; r.z = p2_one();
+  PCoeffs c;
+  const P2 zero = p2_zero();
+  int idx = 0;
+#pragma unroll 1
+  for (int b = BLS_LOOP_TOP; b >= -1; b--) {
+    pg2_doubling_step(r, c);
+    if (inf) { c.c0 = zero; c.c1 = zero; c.c2 = zero; }
+    if (active) st_pcoeffs(o + 36 * idx, c);
+    idx++;
+    if (b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull)) {
+      pg2_addition_step(r, qx, qy, c);
+      if (inf) { c.c0 = zero; c.c1 = zero; c.c2 = zero; }
+      if (active) st_pcoeffs(o + 36 * idx, c);
+      idx++;
+    }
+  }
+  if (active && pair_c() == 0) o[G2P_W - 1] = inf ? 1ull : 0ull;
+}
+
+// the reference's literal miller_loop (mod.rs:40-102) for n independent pairs, coefficients read from memory
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller_prepared(const uint64_t* p, const uint64_t* qp, uint64_t* out, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = t >> 1;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  const uint64_t* pi = p + G1A_W * i;
+  const uint64_t* qi = qp + (size_t)G2P_W * i;
+  const bool live = pi[12] == 0 && qi[G2P_W - 1] == 0;
+  const Fp px = ld_fp(pi), py = ld_fp(pi + 6);
+  P12 f;
+  p12_one(f);
+  PCoeffs c;
+  int idx = 0;
+#pragma unroll 1
+  for (int b = BLS_LOOP_TOP; b >= -1; b--) {
+    ld_pcoeffs(c, qi + 36 * idx); idx++;
+    p_ell(f, c, px, py);
+    if (b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull)) {
+      ld_pcoeffs(c, qi + 36 * idx); idx++;
+      p_ell(f, c, px, py);
+    }
+    if (b >= 0) p12_sqr(f, f);
+  }
+  p12_conjugate(f);
+  if (!live) p12_one(f);
+  if (active) st_p12(out + FQ12_W * i, f);
+}
+
+// ONE miller_loop over n prepared pairs: lane pair t owns pairs t, t+T, ... and one accumulator (see k_pair_multi_miller)
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_multi_miller_prepared(const uint64_t* p, const uint64_t* qp, size_t n, uint64_t* partials) {
+  const size_t T = ((size_t)gridDim.x * blockDim.x) >> 1;
+  const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+  const size_t per = (n + T - 1) / T;
+  P12 f;
+  p12_one(f);
+  PCoeffs c;
+  int idx = 0;
+#pragma unroll 1
+  for (int b = BLS_LOOP_TOP; b >= -1; b--) {
+    const bool bit = b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull);
+#pragma unroll 1
+    for (int rep = 0; rep < (bit ? 2 : 1); rep++) {
+#pragma unroll 1
+      for (size_t j = 0; j < per; j++) {
+        size_t i = t + j * T;
+        const bool in_range = i < n;
+        if (!in_range) i = n - 1;
+        const uint64_t* pi = p + G1A_W * i;
+        const uint64_t* qi = qp + (size_t)G2P_W * i;
+        const bool dead = !in_range || pi[12] != 0 || qi[G2P_W - 1] != 0;
+        ld_pcoeffs(c, qi + 36 * idx);
+        pcoeffs_set_one_if(dead, c);
+        p_ell(f, c, ld_fp(pi), ld_fp(pi + 6));
+      }
+      idx++;
+    }
+    if (b >= 0) p12_sqr(f, f);
+  }
+  p12_conjugate(f);
+  st_p12(partials + FQ12_W * t, f);
+}
+
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_final_exp(const uint64_t* in, uint64_t* out, uint8_t* is_some, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = t >> 1;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  P12 f, g;
+  ld_p12(f, in + FQ12_W * i);
+  bool ok = p_final_exponentiation(g, f);
+  if (active) {
+    st_p12(out + FQ12_W * i, g);
+    if (is_some && pair_c() == 0) is_some[i] = ok;
+  }
+}
+
+// Field::pow on Fq12 with an FrRepr exponent (lib.rs:306-324; GT exponentiation, tests/engine.rs:121):
+// MSB-first square-and-multiply.  The exponent differs per lane pair, so the loop is branch-free over all
+// 256 bits (every lane has to reach every shuffle): squarings and products are computed for the whole warp
+// and committed per lane pair.  Generic squaring (the input need not be in the cyclotomic subgroup).
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_fq12_pow(const uint64_t* in, const uint64_t* k, uint64_t* out, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = t >> 1;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  P12 a, res, tmp;
+  ld_p12(a, in + FQ12_W * i);
+  Scalar s = ld_scalar(k + 4 * i);
+  p12_one(res);
+  bool found = false;
+#pragma unroll 1
+  for (int b = 255; b >= 0; b--) {
+    const bool bit = (s.v[b >> 5] >> (b & 31)) & 1u;
+    if (__any_sync(0xffffffffu, found)) {
+      p12_sqr(tmp, res);
+      p12_select(res, found, tmp, res);
+    }
+    found |= bit;
+    if (__any_sync(0xffffffffu, bit)) {
+      p12_mul(tmp, res, a);
+      p12_select(res, bit, tmp, res);
+    }
+  }
+  if (active) st_p12(out + FQ12_W * i, res);
+}
+
+// Lane-pair form of the multi-pairing Miller loop (the production path of bls_multi_miller_loop*):
+// lane pair t owns pairs t, t+T, ... and ONE accumulator f.  Lane c keeps coefficient c of the running
+// G2 point R_j in the word-major scratch array: word k of pair j's coefficient c at rstate[(c*36+k)*n + j].
+// Every lane has to reach every shuffle, so there is no `continue`: a pair with an infinity member
+// (mod.rs:49-54) or past the end of the batch multiplies f by the sparse element (1, 0, 0) = one instead,
+// which leaves the canonical value of f unchanged.
+__device__ __forceinline__ void ld_pjac_soa(PJac& r, const uint32_t* s, size_t n, size_t pair) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(&r);
+  const uint32_t* b = s + (size_t)pair_c() * 36 * n + pair;
+#pragma unroll
+  for (int k = 0; k < 36; k++) w[k] = b[(size_t)k * n];
+}
+__device__ __forceinline__ void st_pjac_soa(uint32_t* s, size_t n, size_t pair, const PJac& r) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
+  uint32_t* b = s + (size_t)pair_c() * 36 * n + pair;
+#pragma unroll
+  for (int k = 0; k < 36; k++) b[(size_t)k * n] = w[k];
+}
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_multi_miller(const uint64_t* p, const uint64_t* q, size_t n, uint32_t* rstate, uint64_t* partials) {
+  const size_t T = ((size_t)gridDim.x * blockDim.x) >> 1;                       // lane pairs
+  const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+  const size_t per = (n + T - 1) / T;                                            // loop trips, uniform over the grid
+  P12 f;
+  p12_one(f);
+  PCoeffs c;
+  PJac r;
+#pragma unroll 1
+  for (int b = BLS_LOOP_TOP; b >= -1; b--) {   // b == -1 is the trailing doubling step (mod.rs:92-94)
+    const bool bit = b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull);
+#pragma unroll 1
+    for (size_t j = 0; j < per; j++) {
+      size_t i = t + j * T;
+      const bool in_range = i < n;
+      if (!in_range) i = n - 1;
+      const uint64_t* pi = p + G1A_W * i;
+      const uint64_t* qi = q + G2A_W * i;
+      const bool dead = !in_range || pi[12] != 0 || qi[24] != 0;
+      if (b == BLS_LOOP_TOP) { r.x = ld_p2(qi); r.y = ld_p2(qi + 12); r.z = p2_one(); }
+      else ld_pjac_soa(r, rstate, n, i);
+      pg2_doubling_step(r, c);
+      pcoeffs_set_one_if(dead, c);
+      p_ell(f, c, ld_fp(pi), ld_fp(pi + 6));
+      if (b >= 0 && in_range) st_pjac_soa(rstate, n, i, r);
+    }
+    if (bit) {
+#pragma unroll 1
+      for (size_t j = 0; j < per; j++) {
+        size_t i = t + j * T;
+        const bool in_range = i < n;
+        if (!in_range) i = n - 1;
+        const uint64_t* pi = p + G1A_W * i;
+        const uint64_t* qi = q + G2A_W * i;
+        const bool dead = !in_range || pi[12] != 0 || qi[24] != 0;
+        ld_pjac_soa(r, rstate, n, i);
+        pg2_addition_step(r, ld_p2(qi), ld_p2(qi + 12), c);
+        pcoeffs_set_one_if(dead, c);
+        p_ell(f, c, ld_fp(pi), ld_fp(pi + 6));
+        if (in_range) st_pjac_soa(rstate, n, i, r);
+      }
+    }
+    if (b >= 0) p12_sqr(f, f);
+  }
+  p12_conjugate(f);
+  st_p12(partials + FQ12_W * t, f);
+}
+
+extern "C" {
+
+
+int bls_g2_prepare_dev(bls_ctx* ctx, const bls_g2_affine* q, bls_g2_prepared* out, size_t n, void* stream) {
+  if (!ctx || (n && (!q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_pair_g2_prepare<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)q, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream) {
+  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_pair_miller<false><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_miller_loop_prepared_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q, bls_fq12* out, size_t n, void* stream) {
+  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_pair_miller_prepared<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_final_exponentiation_dev(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n, void* stream) {
+  if (!ctx || (n && (!in || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_pair_final_exp<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)in, (uint64_t*)out, is_some, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_pairing_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream) {
+  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_pair_miller<true><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+
+int bls_fq12_pow_dev(bls_ctx* ctx, const bls_fq12* a, const bls_fr_repr* k, bls_fq12* out, size_t n, void* stream) {
+  if (!ctx || (n && (!a || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  k_pair_fq12_pow<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)a, (const uint64_t*)k, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+// lane pairs (= partial products) used by the multi-Miller kernel for n pairs: enough pairs per lane pair to
+// amortise the shared squarings, never more lane pairs than pairs; a multiple of the 64 lane pairs of a block
+static size_t mm_threads(const bls_ctx* ctx, size_t n) {
+  const size_t per_block = BLS_PAIR_TPB / 2;
+  size_t full = (size_t)ctx->sm_count * BLS_PAIR_MINB * per_block;
+  size_t t = n < full ? n : full;
+  t = (t + per_block - 1) / per_block * per_block;
+  return t ? t : per_block;
+}
+size_t bls_multi_miller_scratch_bytes(const bls_ctx* ctx, size_t n) {
+  if (!ctx) return 0;
+  size_t T = mm_threads(ctx, n);
+  return n * 72 * sizeof(uint32_t) + T * sizeof(bls_fq12) + bls_fq12_product_scratch_bytes(ctx, T);
+}
+
+int bls_multi_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, void* scratch, void* stream) {
+  if (!ctx || !out1 || (n && (!p || !q || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = pick(ctx, stream);
+  if (n == 0) {
+    return bls_fq12_product_dev(ctx, nullptr, 0, out1, nullptr, stream);   // the empty product: one
+  }
+  size_t T = mm_threads(ctx, n);
+  uint32_t* rstate = (uint32_t*)scratch;
+  uint64_t* partials = (uint64_t*)((char*)scratch + n * 72 * sizeof(uint32_t));
+  uint64_t* prod_scratch = partials + T * FQ12_W;
+  k_pair_multi_miller<<<(unsigned)(2 * T / BLS_PAIR_TPB), BLS_PAIR_TPB, 0, s>>>((const uint64_t*)p, (const uint64_t*)q, n, rstate, partials);
+  LAUNCH_CHECK();
+  return bls_internal_product_passes(ctx, partials, T, out1, prod_scratch, s);
+}
+
+}  // extern "C"
+
+size_t bls_internal_mm_lane_pairs(const bls_ctx* ctx, size_t n) { return mm_threads(ctx, n); }
+int bls_internal_multi_miller_prepared(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* qp, size_t n, bls_fq12* partials, cudaStream_t s) {
+  const size_t T = mm_threads(ctx, n);
+  k_pair_multi_miller_prepared<<<(unsigned)(2 * T / BLS_PAIR_TPB), BLS_PAIR_TPB, 0, s>>>((const uint64_t*)p, (const uint64_t*)qp, n, (uint64_t*)partials);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}

@@ -48,13 +48,13 @@ __device__ __forceinline__ bool p2_is_zero(const P2& a) {
   return z && __shfl_xor_sync(0xffffffffu, (int)z, 1);
 }
 // x (1 + u) = (c0 - c1) + (c0 + c1) u   (fq2.rs:41-45)
-__device__ __noinline__ P2 p2_mul_by_nonresidue(P2 a) {
+static __device__ __noinline__ P2 p2_mul_by_nonresidue(P2 a) {
   Fp oth = pair_xchg(a.v);
   // lane 0: c0 - c1 = own + (2q - oth);  lane 1: c1 + c0 = own + oth   (one folded addition instead of add, sub, select)
   return P2{fp_add(a.v, fp_select(pair_c() == 0, fp_neg(oth), oth))};
 }
 // fq2.rs:123-136: c0 = a0 b0 - a1 b1, c1 = a0 b1 + a1 b0, one lazily reduced dual product per lane
-__device__ __noinline__ P2 p2_mul(P2 a, P2 b) {
+static __device__ __noinline__ P2 p2_mul(P2 a, P2 b) {
   Fp ao = pair_xchg(a.v), bo = pair_xchg(b.v);
   bool c0 = pair_c() == 0;
   // lane 0: a0 * b0 + (-a1) * b1        lane 1: a0 * b1 + a1 * b0   (X * b_own + Y * b_oth)
@@ -63,7 +63,7 @@ __device__ __noinline__ P2 p2_mul(P2 a, P2 b) {
   return P2{fp_mul2(x, b.v, y, bo)};
 }
 // fq2.rs:87-101: c0 = (a0 + a1)(a0 - a1), c1 = 2 a0 a1
-__device__ __noinline__ P2 p2_sqr(P2 a) {
+static __device__ __noinline__ P2 p2_sqr(P2 a) {
   Fp oth = pair_xchg(a.v);
   bool c0 = pair_c() == 0;
   Fp u = fp_add(fp_select(c0, a.v, oth), oth);           // lane 0: a0 + a1, lane 1: a0 + a0
@@ -73,7 +73,7 @@ __device__ __noinline__ P2 p2_sqr(P2 a) {
 // Fq2 x Fq: both coefficients scaled (mod.rs:61-65)
 __device__ __forceinline__ P2 p2_mul_fp(const P2& a, const Fp& s) { return P2{fp_mul(a.v, s)}; }
 // fq2.rs:138-155; returns false for zero.  Both lanes run the Fq inversion of the norm.
-__device__ __noinline__ bool p2_inv(P2& out, const P2& a) {
+static __device__ __noinline__ bool p2_inv(P2& out, const P2& a) {
   Fp sq = fp_sqr(a.v);
   Fp t = fp_add(sq, pair_xchg(sq));
   Fp ti;
@@ -100,7 +100,7 @@ __device__ __forceinline__ void p6_mul_by_nonresidue(P6& r, const P6& a) {
   r.c2 = a.c1; r.c1 = a.c0; r.c0 = t;
 }
 // fq6.rs:199-248
-__device__ __noinline__ void p6_mul(P6& r, const P6& a, const P6& b) {
+static __device__ __noinline__ void p6_mul(P6& r, const P6& a, const P6& b) {
   P2 aa = p2_mul(a.c0, b.c0), bb = p2_mul(a.c1, b.c1), cc = p2_mul(a.c2, b.c2);
   P2 t1 = p2_mul(p2_add(b.c1, b.c2), p2_add(a.c1, a.c2));
   t1 = p2_add(p2_mul_by_nonresidue(p2_sub(p2_sub(t1, bb), cc)), aa);
@@ -111,7 +111,7 @@ __device__ __noinline__ void p6_mul(P6& r, const P6& a, const P6& b) {
   r.c0 = t1; r.c1 = t2; r.c2 = t3;
 }
 // fq6.rs:166-197
-__device__ __noinline__ void p6_sqr(P6& r, const P6& a) {
+static __device__ __noinline__ void p6_sqr(P6& r, const P6& a) {
   P2 s0 = p2_sqr(a.c0);
   P2 s1 = p2_dbl(p2_mul(a.c0, a.c1));
   P2 s2 = p2_sqr(p2_add(p2_sub(a.c0, a.c1), a.c2));
@@ -122,14 +122,14 @@ __device__ __noinline__ void p6_sqr(P6& r, const P6& a) {
   r.c2 = p2_sub(p2_sub(p2_add(p2_add(s1, s2), s3), s0), s4);
 }
 // fq6.rs:40-66
-__device__ __noinline__ void p6_mul_by_1(P6& r, const P6& a, const P2& c1) {
+static __device__ __noinline__ void p6_mul_by_1(P6& r, const P6& a, const P2& c1) {
   P2 bb = p2_mul(a.c1, c1);
   P2 t1 = p2_mul_by_nonresidue(p2_sub(p2_mul(c1, p2_add(a.c1, a.c2)), bb));
   P2 t2 = p2_sub(p2_mul(c1, p2_add(a.c0, a.c1)), bb);
   r.c0 = t1; r.c1 = t2; r.c2 = bb;
 }
 // fq6.rs:68-109
-__device__ __noinline__ void p6_mul_by_01(P6& r, const P6& a, const P2& c0, const P2& c1) {
+static __device__ __noinline__ void p6_mul_by_01(P6& r, const P6& a, const P2& c0, const P2& c1) {
   P2 aa = p2_mul(a.c0, c0);
   P2 bb = p2_mul(a.c1, c1);
   P2 t1 = p2_add(p2_mul_by_nonresidue(p2_sub(p2_mul(c1, p2_add(a.c1, a.c2)), bb)), aa);
@@ -138,7 +138,7 @@ __device__ __noinline__ void p6_mul_by_01(P6& r, const P6& a, const P2& c0, cons
   r.c0 = t1; r.c1 = t2; r.c2 = t3;
 }
 // fq6.rs:250-301
-__device__ __noinline__ bool p6_inv(P6& r, const P6& a) {
+static __device__ __noinline__ bool p6_inv(P6& r, const P6& a) {
   P2 c0 = p2_add(p2_neg(p2_mul(p2_mul_by_nonresidue(a.c2), a.c1)), p2_sqr(a.c0));
   P2 c1 = p2_sub(p2_mul_by_nonresidue(p2_sqr(a.c2)), p2_mul(a.c0, a.c1));
   P2 c2 = p2_sub(p2_sqr(a.c1), p2_mul(a.c0, a.c2));
@@ -150,7 +150,7 @@ __device__ __noinline__ bool p6_inv(P6& r, const P6& a) {
   return ok;
 }
 // fq6.rs:157-164
-__device__ __noinline__ void p6_frobenius(P6& r, const P6& a, int power) {
+static __device__ __noinline__ void p6_frobenius(P6& r, const P6& a, int power) {
   P2 c0 = p2_frobenius(a.c0, power);
   P2 c1 = p2_mul(p2_frobenius(a.c1, power), p2_from_const(BLS_FROB_FQ6_C1[power % 6]));
   P2 c2 = p2_mul(p2_frobenius(a.c2, power), p2_from_const(BLS_FROB_FQ6_C2[power % 6]));
@@ -165,7 +165,7 @@ __device__ __forceinline__ void p6_select(P6& r, bool take_a, const P6& a, const
 }
 __device__ __forceinline__ void p12_select(P12& r, bool take_a, const P12& a, const P12& b) { p6_select(r.c0, take_a, a.c0, b.c0); p6_select(r.c1, take_a, a.c1, b.c1); }
 // fq12.rs:116-130 (r may alias a or b)
-__device__ __noinline__ void p12_mul(P12& r, const P12& a, const P12& b) {
+static __device__ __noinline__ void p12_mul(P12& r, const P12& a, const P12& b) {
   P6 aa, bb, o, s;
   p6_mul(aa, a.c0, b.c0);
   p6_mul(bb, a.c1, b.c1);
@@ -178,7 +178,7 @@ __device__ __noinline__ void p12_mul(P12& r, const P12& a, const P12& b) {
   p6_add(r.c0, bb, aa);
 }
 // fq12.rs:99-114
-__device__ __noinline__ void p12_sqr(P12& r, const P12& a) {
+static __device__ __noinline__ void p12_sqr(P12& r, const P12& a) {
   P6 ab, c0c1, c0;
   p6_mul(ab, a.c0, a.c1);
   p6_add(c0c1, a.c0, a.c1);
@@ -197,7 +197,7 @@ __device__ __forceinline__ void p4_sqr(P2& t0, P2& t1, const P2& a, const P2& b)
   t0 = p2_sub(p2_sub(s, tmp), p2_mul_by_nonresidue(tmp));
   t1 = p2_dbl(tmp);
 }
-__device__ __noinline__ void p12_cyclotomic_sqr(P12& r, const P12& f) {
+static __device__ __noinline__ void p12_cyclotomic_sqr(P12& r, const P12& f) {
   P2 t0, t1, t2, t3, t4, t5;
   p4_sqr(t0, t1, f.c0.c0, f.c1.c1);
   p4_sqr(t2, t3, f.c1.c0, f.c0.c2);
@@ -213,7 +213,7 @@ __device__ __noinline__ void p12_cyclotomic_sqr(P12& r, const P12& f) {
   r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
 }
 // fq12.rs:34-48
-__device__ __noinline__ void p12_mul_by_014(P12& f, const P2& c0, const P2& c1, const P2& c4) {
+static __device__ __noinline__ void p12_mul_by_014(P12& f, const P2& c0, const P2& c1, const P2& c4) {
   P6 aa, bb, s;
   p6_mul_by_01(aa, f.c0, c0, c1);
   p6_mul_by_1(bb, f.c1, c4);
@@ -226,7 +226,7 @@ __device__ __noinline__ void p12_mul_by_014(P12& f, const P2& c0, const P2& c1, 
   p6_add(f.c0, bb, aa);
 }
 // fq12.rs:132-148
-__device__ __noinline__ bool p12_inv(P12& r, const P12& a) {
+static __device__ __noinline__ bool p12_inv(P12& r, const P12& a) {
   P6 c0s, c1s, t;
   p6_sqr(c0s, a.c0);
   p6_sqr(c1s, a.c1);
@@ -240,7 +240,7 @@ __device__ __noinline__ bool p12_inv(P12& r, const P12& a) {
   return ok;
 }
 // fq12.rs:90-97
-__device__ __noinline__ void p12_frobenius(P12& r, const P12& a, int power) {
+static __device__ __noinline__ void p12_frobenius(P12& r, const P12& a, int power) {
   p6_frobenius(r.c0, a.c0, power);
   p6_frobenius(r.c1, a.c1, power);
   P2 k = p2_from_const(BLS_FROB_FQ12_C1[power % 12]);
@@ -254,7 +254,7 @@ struct PCoeffs { P2 c0, c1, c2; };
 struct PJac { P2 x, y, z; };
 
 // mod.rs:176-245
-__device__ __noinline__ void pg2_doubling_step(PJac& r, PCoeffs& out) {
+static __device__ __noinline__ void pg2_doubling_step(PJac& r, PCoeffs& out) {
   P2 tmp0 = p2_sqr(r.x);
   P2 tmp1 = p2_sqr(r.y);
   P2 tmp2 = p2_sqr(tmp1);
@@ -271,7 +271,7 @@ __device__ __noinline__ void pg2_doubling_step(PJac& r, PCoeffs& out) {
   out.c0 = p2_dbl(p2_mul(r.z, zsq));
 }
 // mod.rs:247-333
-__device__ __noinline__ void pg2_addition_step(PJac& r, const P2& qx, const P2& qy, PCoeffs& out) {
+static __device__ __noinline__ void pg2_addition_step(PJac& r, const P2& qx, const P2& qy, PCoeffs& out) {
   P2 zsq = p2_sqr(r.z);
   P2 ysq = p2_sqr(qy);
   P2 t0 = p2_mul(zsq, qx);
@@ -330,7 +330,7 @@ __device__ __forceinline__ void p_miller_loop_single(P12& f, const Fp& px, const
 // shortcuts (SURVEY.md 8c "latitude"): the leading `one * self` product of pow is a copy, and -- the operand being
 // in the cyclotomic subgroup (exp_by_x is only called after the easy part) -- every squaring is a Granger-Scott
 // cyclotomic squaring.
-__device__ __noinline__ void p12_exp_by_x(P12& out, const P12& a, uint64_t x) {
+static __device__ __noinline__ void p12_exp_by_x(P12& out, const P12& a, uint64_t x) {
   P12 res = a;
   const int top = 63 - __clzll((long long)x);
 #pragma unroll 1

@@ -34,14 +34,14 @@ __device__ __forceinline__ Fp2 fp2_neg(const Fp2& a) { return Fp2{fp_neg(a.c0), 
 __device__ __forceinline__ Fp2 fp2_mul_by_nonresidue(const Fp2& a) { return Fp2{fp_sub(a.c0, a.c1), fp_add(a.c0, a.c1)}; }
 
 // Karatsuba, fq2.rs:123-136
-__device__ __noinline__ Fp2 fp2_mul(Fp2 a, Fp2 b) {
+static __device__ __noinline__ Fp2 fp2_mul(Fp2 a, Fp2 b) {
   Fp aa = fp_mul(a.c0, b.c0);
   Fp bb = fp_mul(a.c1, b.c1);
   Fp s = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
   return Fp2{fp_sub(aa, bb), fp_sub(fp_sub(s, aa), bb)};
 }
 // complex squaring, fq2.rs:87-101
-__device__ __noinline__ Fp2 fp2_sqr(Fp2 a) {
+static __device__ __noinline__ Fp2 fp2_sqr(Fp2 a) {
   Fp ab = fp_mul(a.c0, a.c1);
   Fp t = fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1));
   return Fp2{t, fp_dbl(ab)};
@@ -52,7 +52,7 @@ __device__ __forceinline__ Fp2 fp2_mul_fp(const Fp2& a, const Fp& s) { return Fp
 // a^(q-2) by a fixed 4-bit window over the (compile-time) exponent.  Value-identical to the
 // reference's binary extended Euclid (fq.rs:849-902): the inverse in a field is unique and the
 // result is canonical.  Returns false (and zero) for a == 0, the reference's `None`.
-__device__ __noinline__ bool fp_inv(Fp& out, const Fp& a) {
+static __device__ __noinline__ bool fp_inv(Fp& out, const Fp& a) {
   if (fp_is_zero(a)) { out = fp_zero(); return false; }
   Fp tbl[16];
   tbl[0] = fp_one();
@@ -103,7 +103,7 @@ __device__ __forceinline__ void fp6_mul_by_nonresidue(Fp6& r, const Fp6& a) {
   r.c2 = a.c1; r.c1 = a.c0; r.c0 = t;
 }
 // fq6.rs:199-248
-__device__ __noinline__ void fp6_mul(Fp6& r, const Fp6& a, const Fp6& b) {
+static __device__ __noinline__ void fp6_mul(Fp6& r, const Fp6& a, const Fp6& b) {
   Fp2 aa = fp2_mul(a.c0, b.c0), bb = fp2_mul(a.c1, b.c1), cc = fp2_mul(a.c2, b.c2);
   Fp2 t1 = fp2_mul(fp2_add(b.c1, b.c2), fp2_add(a.c1, a.c2));
   t1 = fp2_add(fp2_mul_by_nonresidue(fp2_sub(fp2_sub(t1, bb), cc)), aa);
@@ -114,7 +114,7 @@ __device__ __noinline__ void fp6_mul(Fp6& r, const Fp6& a, const Fp6& b) {
   r.c0 = t1; r.c1 = t2; r.c2 = t3;
 }
 // fq6.rs:166-197
-__device__ __noinline__ void fp6_sqr(Fp6& r, const Fp6& a) {
+static __device__ __noinline__ void fp6_sqr(Fp6& r, const Fp6& a) {
   Fp2 s0 = fp2_sqr(a.c0);
   Fp2 s1 = fp2_dbl(fp2_mul(a.c0, a.c1));
   Fp2 s2 = fp2_sqr(fp2_add(fp2_sub(a.c0, a.c1), a.c2));
@@ -125,14 +125,14 @@ __device__ __noinline__ void fp6_sqr(Fp6& r, const Fp6& a) {
   r.c2 = fp2_sub(fp2_sub(fp2_add(fp2_add(s1, s2), s3), s0), s4);
 }
 // fq6.rs:40-66
-__device__ __noinline__ void fp6_mul_by_1(Fp6& r, const Fp6& a, const Fp2& c1) {
+static __device__ __noinline__ void fp6_mul_by_1(Fp6& r, const Fp6& a, const Fp2& c1) {
   Fp2 bb = fp2_mul(a.c1, c1);
   Fp2 t1 = fp2_mul_by_nonresidue(fp2_sub(fp2_mul(c1, fp2_add(a.c1, a.c2)), bb));
   Fp2 t2 = fp2_sub(fp2_mul(c1, fp2_add(a.c0, a.c1)), bb);
   r.c0 = t1; r.c1 = t2; r.c2 = bb;
 }
 // fq6.rs:68-109
-__device__ __noinline__ void fp6_mul_by_01(Fp6& r, const Fp6& a, const Fp2& c0, const Fp2& c1) {
+static __device__ __noinline__ void fp6_mul_by_01(Fp6& r, const Fp6& a, const Fp2& c0, const Fp2& c1) {
   Fp2 aa = fp2_mul(a.c0, c0);
   Fp2 bb = fp2_mul(a.c1, c1);
   Fp2 t1 = fp2_add(fp2_mul_by_nonresidue(fp2_sub(fp2_mul(c1, fp2_add(a.c1, a.c2)), bb)), aa);
@@ -141,7 +141,7 @@ __device__ __noinline__ void fp6_mul_by_01(Fp6& r, const Fp6& a, const Fp2& c0, 
   r.c0 = t1; r.c1 = t2; r.c2 = t3;
 }
 // fq6.rs:250-301
-__device__ __noinline__ bool fp6_inv(Fp6& r, const Fp6& a) {
+static __device__ __noinline__ bool fp6_inv(Fp6& r, const Fp6& a) {
   Fp2 c0 = fp2_add(fp2_neg(fp2_mul(fp2_mul_by_nonresidue(a.c2), a.c1)), fp2_sqr(a.c0));
   Fp2 c1 = fp2_sub(fp2_mul_by_nonresidue(fp2_sqr(a.c2)), fp2_mul(a.c0, a.c1));
   Fp2 c2 = fp2_sub(fp2_sqr(a.c1), fp2_mul(a.c0, a.c2));
@@ -153,7 +153,7 @@ __device__ __noinline__ bool fp6_inv(Fp6& r, const Fp6& a) {
   return ok;
 }
 // fq6.rs:157-164
-__device__ __noinline__ void fp6_frobenius(Fp6& r, const Fp6& a, int power) {
+static __device__ __noinline__ void fp6_frobenius(Fp6& r, const Fp6& a, int power) {
   Fp2 c0 = fp2_frobenius(a.c0, power);
   Fp2 c1 = fp2_mul(fp2_frobenius(a.c1, power), fp2_from_const(BLS_FROB_FQ6_C1[power % 6]));
   Fp2 c2 = fp2_mul(fp2_frobenius(a.c2, power), fp2_from_const(BLS_FROB_FQ6_C2[power % 6]));
@@ -166,7 +166,7 @@ __device__ __forceinline__ bool fp12_is_zero(const Fp12& a) { return fp6_is_zero
 // fq12.rs:30-32
 __device__ __forceinline__ void fp12_conjugate(Fp12& a) { fp6_neg(a.c1, a.c1); }
 // fq12.rs:116-130 (r may alias a or b)
-__device__ __noinline__ void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
+static __device__ __noinline__ void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
   Fp6 aa, bb, o, s;
   fp6_mul(aa, a.c0, b.c0);
   fp6_mul(bb, a.c1, b.c1);
@@ -179,7 +179,7 @@ __device__ __noinline__ void fp12_mul(Fp12& r, const Fp12& a, const Fp12& b) {
   fp6_add(r.c0, bb, aa);
 }
 // fq12.rs:99-114 (generic complex squaring; r may alias a)
-__device__ __noinline__ void fp12_sqr(Fp12& r, const Fp12& a) {
+static __device__ __noinline__ void fp12_sqr(Fp12& r, const Fp12& a) {
   Fp6 ab, c0c1, c0;
   fp6_mul(ab, a.c0, a.c1);
   fp6_add(c0c1, a.c0, a.c1);
@@ -201,7 +201,7 @@ __device__ __forceinline__ void fp4_sqr(Fp2& t0, Fp2& t1, const Fp2& a, const Fp
   t0 = fp2_sub(fp2_sub(s, tmp), fp2_mul_by_nonresidue(tmp));   // a^2 + xi b^2
   t1 = fp2_dbl(tmp);                                           // 2ab
 }
-__device__ __noinline__ void fp12_cyclotomic_sqr(Fp12& r, const Fp12& f) {
+static __device__ __noinline__ void fp12_cyclotomic_sqr(Fp12& r, const Fp12& f) {
   Fp2 t0, t1, t2, t3, t4, t5;
   fp4_sqr(t0, t1, f.c0.c0, f.c1.c1);
   fp4_sqr(t2, t3, f.c1.c0, f.c0.c2);
@@ -218,7 +218,7 @@ __device__ __noinline__ void fp12_cyclotomic_sqr(Fp12& r, const Fp12& f) {
   r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
 }
 // fq12.rs:34-48 (in place on f)
-__device__ __noinline__ void fp12_mul_by_014(Fp12& f, const Fp2& c0, const Fp2& c1, const Fp2& c4) {
+static __device__ __noinline__ void fp12_mul_by_014(Fp12& f, const Fp2& c0, const Fp2& c1, const Fp2& c4) {
   Fp6 aa, bb, s;
   fp6_mul_by_01(aa, f.c0, c0, c1);
   fp6_mul_by_1(bb, f.c1, c4);
@@ -231,7 +231,7 @@ __device__ __noinline__ void fp12_mul_by_014(Fp12& f, const Fp2& c0, const Fp2& 
   fp6_add(f.c0, bb, aa);
 }
 // fq12.rs:132-148
-__device__ __noinline__ bool fp12_inv(Fp12& r, const Fp12& a) {
+static __device__ __noinline__ bool fp12_inv(Fp12& r, const Fp12& a) {
   Fp6 c0s, c1s, t;
   fp6_sqr(c0s, a.c0);
   fp6_sqr(c1s, a.c1);
@@ -245,7 +245,7 @@ __device__ __noinline__ bool fp12_inv(Fp12& r, const Fp12& a) {
   return ok;
 }
 // fq12.rs:90-97 (r may alias a)
-__device__ __noinline__ void fp12_frobenius(Fp12& r, const Fp12& a, int power) {
+static __device__ __noinline__ void fp12_frobenius(Fp12& r, const Fp12& a, int power) {
   fp6_frobenius(r.c0, a.c0, power);
   fp6_frobenius(r.c1, a.c1, power);
   Fp2 k = fp2_from_const(BLS_FROB_FQ12_C1[power % 12]);

@@ -7,26 +7,31 @@ use std::process::Command;
 fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("..");
-    let src = root.join("pairing_b200/csrc/kernels.cu");
     let lib = out.join("libpairing_b200.a");
-    let obj = out.join("kernels.o");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
-    let status = Command::new(&nvcc)
-        .args(&["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-                "-Xcompiler", "-fPIC", "-c", "-o"])
-        .arg(&obj)
-        .arg(&src)
-        .status()
-        .expect("nvcc not found: set NVCC");
-    assert!(status.success(), "nvcc failed");
-    let status = Command::new("ar").args(&["crs"]).arg(&lib).arg(&obj).status().expect("ar");
+    // two translation units: the lane-pair pairing engine is compiled on its own (pairing_b200/csrc/abi_common.cuh)
+    let mut objs = Vec::new();
+    for unit in &["kernels", "kernels_pair"] {
+        let src = root.join(format!("pairing_b200/csrc/{}.cu", unit));
+        let obj = out.join(format!("{}.o", unit));
+        let status = Command::new(&nvcc)
+            .args(&["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                    "-Xcompiler", "-fPIC", "-c", "-o"])
+            .arg(&obj)
+            .arg(&src)
+            .status()
+            .expect("nvcc not found: set NVCC");
+        assert!(status.success(), "nvcc failed");
+        objs.push(obj);
+    }
+    let status = Command::new("ar").args(&["crs"]).arg(&lib).args(&objs).status().expect("ar");
     assert!(status.success());
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=static=pairing_b200");
     println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
-    for f in &["kernels.cu", "fp.cuh", "tower.cuh", "curve.cuh", "pair_tower.cuh", "codec.cuh", "constants.cuh"] {
+    for f in &["kernels.cu", "kernels_pair.cu", "abi_common.cuh", "fp.cuh", "tower.cuh", "curve.cuh", "pair_tower.cuh", "codec.cuh", "constants.cuh"] {
         println!("cargo:rerun-if-changed={}", root.join("pairing_b200/csrc").join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include/pairing_b200.h").display());
