@@ -36,6 +36,7 @@ typedef struct { bls_fq x, y, z; } bls_g1;                         /* 144 B; Jac
 typedef struct { bls_fq2 x, y; uint64_t infinity; } bls_g2_affine; /* 200 B */
 typedef struct { bls_fq2 x, y, z; } bls_g2;                        /* 288 B */
 typedef struct { uint64_t l[4]; } bls_fr_repr;                     /* 32 B */
+typedef struct { uint64_t l[4]; } bls_fr;                          /* Fr(FrRepr): Montgomery form (x * 2^256 mod r), < r; fr.rs:54-58 */
 /* G2Prepared (ec.rs:1615-1619): 68 = 63 doubling + 5 addition coefficient triples in loop order */
 typedef struct { bls_fq2 coeffs[68][3]; uint64_t infinity; } bls_g2_prepared; /* 19 592 B */
 
@@ -150,6 +151,11 @@ enum {
   BLS_OP_MUL_BY_1 = 16    /* Fq6 only: b.c1 (fq6.rs:40-66) */
 };
 int bls_field_op_batch(bls_ctx*, int degree, int op, const void* a, const void* b, void* out, uint8_t* ok, size_t n);
+
+/* The scalar field Fr (fr.rs:324-572), element-wise: op is BLS_OP_ADD / SUB / MUL / SQR / NEG / DBL / INV /
+ * FROM_REPR (bls_fr_repr -> bls_fr; ok = 0 for values >= r) / INTO_REPR (bls_fr -> bls_fr_repr).  The step after the
+ * path: callers combine scalars (c * d in the reference's bilinearity test, tests/engine.rs:117-119). */
+int bls_fr_op_batch(bls_ctx*, int op, const bls_fr* a, const bls_fr* b, bls_fr* out, uint8_t* ok, size_t n);
 
 /* ------------------------------------------------------------------ device-pointer variants
  * Same semantics; every pointer is a device pointer on the context's device, the work is enqueued

@@ -12,6 +12,7 @@
 //                                                                  into_compressed, into_uncompressed }
 //   EncodedPoint      src/lib.rs:236-263      -> G1Compressed, G1Uncompressed, G2Compressed, G2Uncompressed
 //   Wnaf              src/wnaf.rs:75-179      -> class Wnaf<G>  { scalar(k).base(g) | base(g, n).scalar(k) }
+//   PrimeField (Fr)   bls12_381/fr.rs:271-572 -> struct FrField { from_repr, into_repr, add/sub/mul_assign, square, inverse, ... }
 // Every value is a BATCH (std::vector of the ABI's POD structs): slice-level entry points are what a GPU is for.
 // `Option` becomes std::optional, `Result<_, GroupDecodingError>` a per-element status; failures of the device layer
 // throw pairing_b200::Error (nothing unwinds across the C ABI itself).  There is no CPU fallback.
@@ -143,6 +144,39 @@ struct Bls12 {
     g.check(bls_fq12_product(g.ctx(), f.data(), f.size(), &out));
     return out;
   }
+};
+
+// ------------------------------------------------------------------------------------------------ scalar field
+// PrimeField / Field for Fr (fr.rs:271-572), batch-shaped.  Values are Montgomery-form `bls_fr`; `from_repr` returns the
+// per-element validity the reference reports as Err(NotInField).
+struct FrField {
+  using Elem = bls_fr;
+  static std::vector<Elem> op(Gpu& g, int o, const std::vector<Elem>& a, const std::vector<Elem>* b, std::vector<uint8_t>* ok = nullptr) {
+    std::vector<Elem> out(a.size());
+    std::vector<uint8_t> good(a.size());
+    g.check(bls_fr_op_batch(g.ctx(), o, a.data(), b ? b->data() : nullptr, out.data(), good.data(), a.size()));
+    if (ok) *ok = good;
+    return out;
+  }
+  static std::vector<Elem> from_repr(Gpu& g, const std::vector<FrRepr>& r, std::vector<uint8_t>* ok = nullptr) {
+    std::vector<Elem> a(r.size());
+    std::memcpy(a.data(), r.data(), r.size() * sizeof(FrRepr));
+    return op(g, BLS_OP_FROM_REPR, a, nullptr, ok);
+  }
+  static std::vector<FrRepr> into_repr(Gpu& g, const std::vector<Elem>& a) {
+    auto o = op(g, BLS_OP_INTO_REPR, a, nullptr);
+    std::vector<FrRepr> r(a.size());
+    std::memcpy(r.data(), o.data(), a.size() * sizeof(FrRepr));
+    return r;
+  }
+  static std::vector<Elem> add_assign(Gpu& g, const std::vector<Elem>& a, const std::vector<Elem>& b) { return op(g, BLS_OP_ADD, a, &b); }
+  static std::vector<Elem> sub_assign(Gpu& g, const std::vector<Elem>& a, const std::vector<Elem>& b) { return op(g, BLS_OP_SUB, a, &b); }
+  static std::vector<Elem> mul_assign(Gpu& g, const std::vector<Elem>& a, const std::vector<Elem>& b) { return op(g, BLS_OP_MUL, a, &b); }
+  static std::vector<Elem> square(Gpu& g, const std::vector<Elem>& a) { return op(g, BLS_OP_SQR, a, nullptr); }
+  static std::vector<Elem> negate(Gpu& g, const std::vector<Elem>& a) { return op(g, BLS_OP_NEG, a, nullptr); }
+  static std::vector<Elem> double_(Gpu& g, const std::vector<Elem>& a) { return op(g, BLS_OP_DBL, a, nullptr); }
+  // Field::inverse: ok[i] == 0 is the reference's None (zero has no inverse)
+  static std::vector<Elem> inverse(Gpu& g, const std::vector<Elem>& a, std::vector<uint8_t>* ok = nullptr) { return op(g, BLS_OP_INV, a, nullptr, ok); }
 };
 
 // ------------------------------------------------------------------------------------------------ curves

@@ -882,3 +882,35 @@ def encode_point(p, g2, compressed):
     if compressed:
         b[0] |= 0x80
     return bytes(b)
+
+
+# ----------------------------------------------------------------------------------------------
+# The scalar field Fr (bls12_381/fr.rs:324-572), Montgomery form with R = 2^256 -- the step after the path
+# (SURVEY.md 8f item 4).  Pinned by the reference's Montgomery-form KATs (fr.rs:1240-1260, 1306-1323, 1450-1486).
+# ----------------------------------------------------------------------------------------------
+FR_MONT_R = (1 << 256) % R_ORDER            # fr.rs:20-26
+FR_MONT_R2 = pow(1 << 256, 2, R_ORDER)      # fr.rs:28-34
+FR_INV64 = (-pow(R_ORDER, -1, 1 << 64)) % (1 << 64)   # fr.rs:36
+FR_RINV = pow(FR_MONT_R, -1, R_ORDER)
+
+
+def fr_to_mont(x): return x * FR_MONT_R % R_ORDER
+def fr_from_mont(x): return x * FR_RINV % R_ORDER
+
+
+def fr_op_mont(op, a, b=None):
+    """The reference's Fr operation on MONTGOMERY-FORM integers a, b (< r).  Returns (value, ok)."""
+    if op == "add": return (a + b) % R_ORDER, True
+    if op == "sub": return (a - b) % R_ORDER, True
+    if op == "mul": return a * b * FR_RINV % R_ORDER, True
+    if op == "sqr": return a * a * FR_RINV % R_ORDER, True
+    if op == "neg": return (-a) % R_ORDER, True
+    if op == "dbl": return 2 * a % R_ORDER, True
+    if op == "inv":
+        if a == 0:
+            return 0, False
+        return fr_to_mont(pow(fr_from_mont(a), -1, R_ORDER)), True
+    if op == "from_repr":                       # a is a canonical integer (possibly >= r): fr.rs:279-288
+        return (fr_to_mont(a), True) if a < R_ORDER else (0, False)
+    if op == "into_repr": return fr_from_mont(a), True
+    raise ValueError(op)

@@ -37,7 +37,7 @@ SYMBOLS = [
     "bls_g1_wnaf_mul_dev", "bls_g2_wnaf_mul_dev", "bls_batch_normalization_scratch_bytes",
     "bls_g1_batch_normalization_dev", "bls_g2_batch_normalization_dev", "bls_imad_peak",
     "bls_g1_wnaf_fixed_base_batch", "bls_g2_wnaf_fixed_base_batch", "bls_g1_wnaf_table", "bls_g2_wnaf_table",
-    "bls_fq12_pow_batch", "bls_fq12_pow_dev",
+    "bls_fq12_pow_batch", "bls_fq12_pow_dev", "bls_fr_op_batch",
     "bls_g1_decode_batch", "bls_g2_decode_batch", "bls_g1_encode_batch", "bls_g2_encode_batch",
     "bls_g1_wnaf_table_dev", "bls_g2_wnaf_table_dev", "bls_g1_wnaf_fixed_base_dev", "bls_g2_wnaf_fixed_base_dev",
 ]
@@ -111,6 +111,7 @@ def load():
         "bls_g2_decode_batch": [vp, vp, ci, ci, vp, vp, sz],
         "bls_g1_encode_batch": [vp, vp, ci, vp, sz],
         "bls_g2_encode_batch": [vp, vp, ci, vp, sz],
+        "bls_fr_op_batch": [vp, ci, vp, vp, vp, vp, sz],
         "bls_fq12_pow_batch": [vp, vp, vp, vp, sz],
         "bls_fq12_pow_dev": [vp, vp, vp, vp, sz, vp],
         "bls_g2_prepare_dev": [vp, vp, vp, sz, vp],
@@ -368,6 +369,16 @@ class Context:
         return out, ok
 
     # ------------------------------------------------------------------ device pointers
+    def fr_op(self, op, a, b=None):
+        """Fr field operation (Montgomery-form (n,4) arrays; from_repr/into_repr convert) -> (values, ok)."""
+        a = _arr(a, W_FR, "a")
+        if b is not None:
+            b = _arr(b, W_FR, "b")
+        out = np.zeros_like(a)
+        ok = np.zeros(a.shape[0], dtype=np.uint8)
+        self._check(self._lib.bls_fr_op_batch(self._ctx, OPS[op], _p(a), _p(b) if b is not None else None, _p(out), _p(ok), a.shape[0]))
+        return out, ok
+
     def call_dev(self, name, *args):
         """Raw access to a `*_dev` entry point: args are ints (device pointers / sizes / stream)."""
         self._check(getattr(self._lib, name)(self._ctx, *args))

@@ -10,6 +10,7 @@
 
 #include "curve.cuh"
 #include "codec.cuh"
+#include "fr.cuh"
 
 __device__ __forceinline__ void ld_F(Fp& r, const uint64_t* p) { r = ld_fp(p); }
 __device__ __forceinline__ void ld_F(Fp2& r, const uint64_t* p) { r = ld_fp2(p); }
@@ -61,6 +62,39 @@ __global__ void __launch_bounds__(128) k_fq_op(int op, const uint64_t* a, const 
     }
   }
   st_fp(out + 6 * i, r);
+  if (ok) ok[i] = good;
+}
+
+// scalar field Fr (fr.rs:324-572): `b` may be NULL for unary operations
+__global__ void __launch_bounds__(128) k_fr_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint8_t* ok, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr x, y = fr_zero(), r = fr_zero();
+  {
+    const uint2* q = reinterpret_cast<const uint2*>(a + 4 * i);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { uint2 t = q[k]; x.v[2 * k] = t.x; x.v[2 * k + 1] = t.y; }
+    if (b) {
+      const uint2* qb = reinterpret_cast<const uint2*>(b + 4 * i);
+#pragma unroll
+      for (int k = 0; k < 4; k++) { uint2 t = qb[k]; y.v[2 * k] = t.x; y.v[2 * k + 1] = t.y; }
+    }
+  }
+  bool good = true;
+  switch (op) {
+    case BLS_OP_ADD: r = fr_add(x, y); break;
+    case BLS_OP_SUB: r = fr_sub(x, y); break;
+    case BLS_OP_MUL: r = fr_mul(x, y); break;
+    case BLS_OP_SQR: r = fr_sqr(x); break;
+    case BLS_OP_NEG: r = fr_neg(x); break;
+    case BLS_OP_DBL: r = fr_add(x, x); break;
+    case BLS_OP_INV: good = fr_inv(r, x); break;
+    case BLS_OP_FROM_REPR: good = !fr_geq(x, fr_modulus()); r = good ? fr_mul(x, fr_r2()) : fr_zero(); break;   // fr.rs:279-288
+    case BLS_OP_INTO_REPR: { Fr one = fr_zero(); one.v[0] = 1; r = fr_mul(x, one); break; }                     // fr.rs:290-303
+  }
+  uint2* o = reinterpret_cast<uint2*>(out + 4 * i);
+#pragma unroll
+  for (int k = 0; k < 4; k++) o[k] = make_uint2(r.v[2 * k], r.v[2 * k + 1]);
   if (ok) ok[i] = good;
 }
 
@@ -983,6 +1017,25 @@ int bls_field_op_batch(bls_ctx* ctx, int degree, int op, const void* a, const vo
   }
   LAUNCH_CHECK();
   D2H(out, dout, n * eb);
+  if (ok) D2H(ok, dok, n);
+  SYNC();
+  return BLS_OK;
+}
+
+int bls_fr_op_batch(bls_ctx* ctx, int op, const bls_fr* a, const bls_fr* b, bls_fr* out, uint8_t* ok, size_t n) {
+  if (!ctx || (n && (!a || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  const bool binary = op == BLS_OP_ADD || op == BLS_OP_SUB || op == BLS_OP_MUL;
+  const bool unary = op == BLS_OP_SQR || op == BLS_OP_NEG || op == BLS_OP_DBL || op == BLS_OP_INV || op == BLS_OP_FROM_REPR || op == BLS_OP_INTO_REPR;
+  if ((!binary && !unary) || (binary && n && !b)) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  H2D(da, a, n * sizeof(*a));
+  H2D(db, binary ? b : nullptr, binary ? n * sizeof(*b) : 1);
+  DALLOC(dout, n * sizeof(*out));
+  DALLOC(dok, n);
+  k_fr_op<<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>(op, (const uint64_t*)da.p, binary ? (const uint64_t*)db.p : nullptr, (uint64_t*)dout.p, (uint8_t*)dok.p, n);
+  LAUNCH_CHECK();
+  D2H(out, dout, n * sizeof(*out));
   if (ok) D2H(ok, dok, n);
   SYNC();
   return BLS_OK;

@@ -31,7 +31,7 @@ fn main() {
     println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
-    for f in &["kernels.cu", "kernels_pair.cu", "abi_common.cuh", "fp.cuh", "tower.cuh", "curve.cuh", "pair_tower.cuh", "codec.cuh", "constants.cuh"] {
+    for f in &["kernels.cu", "kernels_pair.cu", "abi_common.cuh", "fr.cuh", "fp.cuh", "tower.cuh", "curve.cuh", "pair_tower.cuh", "codec.cuh", "constants.cuh"] {
         println!("cargo:rerun-if-changed={}", root.join("pairing_b200/csrc").join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include/pairing_b200.h").display());

@@ -138,10 +138,21 @@ static void random_bilinearity_tests(Gpu& g) {
   auto bc = G2::mul_assign(g, b, c), bd = G2::mul_assign(g, b, d);
   auto acbd = Bls12::pairing(g, G1::into_affine(g, ac), G2::into_affine(g, bd));
   auto adbc = Bls12::pairing(g, G1::into_affine(g, ad), G2::into_affine(g, bc));
-  // e(a, b)^(cd) as (e(a, b)^c)^d: the scalar-field product of the reference test is outside this path
-  auto abcd = Bls12::pow(g, Bls12::pow(g, Bls12::pairing(g, G1::into_affine(g, a), G2::into_affine(g, b)), c), d);
+  // let mut cd = c; cd.mul_assign(&d); e(a, b).pow(cd.into_repr())
+  auto cd = FrField::into_repr(g, FrField::mul_assign(g, FrField::from_repr(g, c), FrField::from_repr(g, d)));
+  auto eab = Bls12::pairing(g, G1::into_affine(g, a), G2::into_affine(g, b));
+  auto abcd = Bls12::pow(g, eab, cd);
   CHECK(same(acbd, adbc));
   CHECK(same(acbd, abcd));
+  CHECK(same(abcd, Bls12::pow(g, Bls12::pow(g, eab, c), d)));
+  // a * a^-1 == 1 and 0 has no inverse (fr.rs:1342-1357)
+  auto cm = FrField::from_repr(g, c);
+  std::vector<uint8_t> ok;
+  auto ci = FrField::inverse(g, cm, &ok);
+  auto one = FrField::from_repr(g, std::vector<FrRepr>(n, FrRepr{{1, 0, 0, 0}}));
+  CHECK(same(FrField::mul_assign(g, cm, ci), one));
+  FrField::inverse(g, std::vector<bls_fr>(1, bls_fr{{0, 0, 0, 0}}), &ok);
+  CHECK(ok[0] == 0);
   CHECK(!(acbd[0] == fq12_one()));
 }
 

@@ -285,3 +285,26 @@ def test_fq12_pow_and_bilinearity(ctx):
     assert not np.array_equal(lhs, one)
     r = np.repeat(np.array([m.limbs64(m.R_ORDER, 4)], dtype=np.uint64), n, 0)     # GT has order r
     eq(ctx.fq12_pow(lhs, r), one)
+
+
+@pytest.mark.parametrize("op", ["add", "sub", "mul", "sqr", "neg", "dbl", "inv", "from_repr", "into_repr"])
+def test_fr_ops(ctx, op):
+    """The scalar field Fr (fr.rs:324-572) against the big-int model, edge values included, plus the reference's KATs."""
+    L = lambda v: m.limbs64(v, 4)
+    edge = [0, 1, 2, m.R_ORDER - 1, m.R_ORDER - 2, m.FR_MONT_R, (m.R_ORDER - 1) // 2, (m.R_ORDER + 1) // 2, 1 << 254, (1 << 255) - 19 - (1 << 254)]
+    edge = [v % m.R_ORDER for v in edge]
+    rnd = dg.rand_scalars(600, 70, edge_cases=False)
+    a = np.concatenate([np.array([L(v) for v in edge], dtype=np.uint64), rnd])
+    b = np.concatenate([np.array([L(v) for v in edge[::-1]], dtype=np.uint64), dg.rand_scalars(600, 71, edge_cases=False)])
+    if op == "from_repr":
+        extra = np.array([L(m.R_ORDER), L(m.R_ORDER + 1), L((1 << 256) - 1)], dtype=np.uint64)
+        a = np.concatenate([a, extra]); b = np.concatenate([b, extra])
+    binary = op in ("add", "sub", "mul")
+    got, gok = ctx.fr_op(op, a, b if binary else None)
+    for i in range(len(a)):
+        want, wok = m.fr_op_mont(op, m.from_limbs64(a[i]), m.from_limbs64(b[i]) if binary else None)
+        assert m.from_limbs64(got[i]) == want and bool(gok[i]) == wok, (op, i)
+    if op == "mul":     # fr.rs:1240-1260
+        x = np.array([[0x6b7e9b8faeefc81a, 0xe30a8463f348ba42, 0xeff3cb67a8279c9c, 0x3d303651bd7c774d]], dtype=np.uint64)
+        y = np.array([[0x13ae28e3bc35ebeb, 0xa10f4488075cae2c, 0x8160e95a853c3b5d, 0x5ae3f03b561a841d]], dtype=np.uint64)
+        assert ctx.fr_op("mul", x, y)[0].tolist() == [[0x23717213ce710f71, 0xdbee1fe53a16e1af, 0xf565d3e1c2a48000, 0x4426507ee75df9d7]]

@@ -344,3 +344,24 @@ def test_model_rejects_invalid_encodings(g2):
         enc = m.encode_point(p, g2, compressed)
         assert m.decode_point(enc, g2, compressed, checked=False) == (m.DEC_OK, p)
         assert m.decode_point(enc, g2, compressed)[0] == m.DEC_NOT_IN_SUBGROUP
+
+
+def test_fr_constants_and_kats():
+    """fr.rs:20-36 (R, R2, INV) and the Montgomery-form KATs of fr.rs:1240-1260 (mul), 1306-1323 (square), 1450-1486 (repr)"""
+    L = m.from_limbs64
+    assert m.FR_MONT_R == L([0x1fffffffe, 0x5884b7fa00034802, 0x998c4fefecbc4ff5, 0x1824b159acc5056f])
+    assert m.FR_MONT_R2 == L([0xc999e990f3f29c6d, 0x2b6cedcb87925c23, 0x5d314967254398f, 0x748d9d99f59ff11])
+    assert m.FR_INV64 == 0xfffffffeffffffff
+    a = L([0x6b7e9b8faeefc81a, 0xe30a8463f348ba42, 0xeff3cb67a8279c9c, 0x3d303651bd7c774d])
+    b = L([0x13ae28e3bc35ebeb, 0xa10f4488075cae2c, 0x8160e95a853c3b5d, 0x5ae3f03b561a841d])
+    assert m.fr_op_mont("mul", a, b)[0] == L([0x23717213ce710f71, 0xdbee1fe53a16e1af, 0xf565d3e1c2a48000, 0x4426507ee75df9d7])
+    s = L([0xffffffffffffffff, 0xffffffffffffffff, 0xffffffffffffffff, 0x73eda753299d7d47])
+    want = m.fr_op_mont("from_repr", L([0xc0d698e7bde077b8, 0xb79a310579e76ec2, 0xac1da8d0a9af4e5f, 0x13f629c49bf23e97]))[0]
+    assert m.fr_op_mont("sqr", s)[0] == want
+    ra = L([0x25ebe3a3ad3c0c6a, 0x6990e39d092e817c, 0x941f900d42f5658e, 0x44f8a103b38a71e0])
+    rb = L([0x264e9454885e2475, 0x46f7746bb0308370, 0x4683ef5347411f9, 0x58838d7f208d4492])
+    rc = L([0x48a09ab93cfc740d, 0x3a6600fbfc7a671, 0x838567017501d767, 0x7161d6da77745512])
+    prod = m.fr_op_mont("mul", m.fr_op_mont("from_repr", ra)[0], m.fr_op_mont("from_repr", rb)[0])[0]
+    assert m.fr_op_mont("into_repr", prod)[0] == rc
+    assert m.fr_op_mont("from_repr", m.R_ORDER) == (0, False) and m.fr_op_mont("from_repr", m.R_ORDER + 1) == (0, False)
+    assert m.fr_op_mont("inv", 0) == (0, False)
