@@ -138,6 +138,14 @@ int bls_g2_decode_batch(bls_ctx*, const uint8_t* bytes, int compressed, int chec
 int bls_g1_encode_batch(bls_ctx*, const bls_g1_affine* in, int compressed, uint8_t* bytes, size_t n);
 int bls_g2_encode_batch(bls_ctx*, const bls_g2_affine* in, int compressed, uint8_t* bytes, size_t n);
 
+/* G::rand with the randomness supplied by the caller (ec.rs:199-214): $affine::get_point_from_x (ec.rs:102-123; is_some = 0
+ * when x^3 + b has no square root) and $affine::scale_by_cofactor (mul_bits with the cofactor, ec.rs:86-94, 871-875,
+ * 1564-1578: Jacobian output, infinity possible -- the reference retries). */
+int bls_g1_point_from_x_batch(bls_ctx*, const bls_fq* x, const uint8_t* greatest, bls_g1_affine* out, uint8_t* is_some, size_t n);
+int bls_g2_point_from_x_batch(bls_ctx*, const bls_fq2* x, const uint8_t* greatest, bls_g2_affine* out, uint8_t* is_some, size_t n);
+int bls_g1_scale_by_cofactor_batch(bls_ctx*, const bls_g1_affine* in, bls_g1* out, size_t n);
+int bls_g2_scale_by_cofactor_batch(bls_ctx*, const bls_g2_affine* in, bls_g2* out, size_t n);
+
 /* ------------------------------------------------------------------ field tower (host buffers) */
 /* Element-wise field operations, the `Field` trait methods of src/lib.rs:267-325 on
  * Fq (degree 1), Fq2 (2), Fq6 (6), Fq12 (12).  `b` is an array of the same element type or NULL.

@@ -914,3 +914,26 @@ def fr_op_mont(op, a, b=None):
         return (fr_to_mont(a), True) if a < R_ORDER else (0, False)
     if op == "into_repr": return fr_from_mont(a), True
     raise ValueError(op)
+
+
+# ----------------------------------------------------------------------------------------------
+# G::rand minus the random number generator (ec.rs:199-214): get_point_from_x (above) then scale_by_cofactor
+# (ec.rs:86-94 mul_bits, cofactors ec.rs:871-875 / 1564-1578); the caller retries on None / infinity.
+# ----------------------------------------------------------------------------------------------
+G1_COFACTOR = from_limbs64([0x8c00aaab0000aaab, 0x396c8c005555e156])
+G2_COFACTOR = from_limbs64([0xcf1c38e31c7238e5, 0x1616ec6e786f0c70, 0x21537e293a6691ae, 0xa628f1cb4d9e82ef,
+                            0xa68a205b2e5a7ddf, 0xcd91de4547085aba, 0x91d50792876a202, 0x5d543a95414e7f1])
+assert G1_COFACTOR == 76329603384216526031706109802092473003
+
+
+def scale_by_cofactor(p, g2):
+    """affine p -> Jacobian [h]p by the reference's mul_bits: MSB-first over ALL bits of the limb array, mixed additions."""
+    F = _F2 if g2 else _F1
+    res = pt_zero(F)
+    nbits = 512 if g2 else 128
+    cof = G2_COFACTOR if g2 else G1_COFACTOR
+    for i in range(nbits - 1, -1, -1):
+        res = pt_double(F, res)
+        if (cof >> i) & 1:
+            res = pt_add_mixed(F, res, p)
+    return res

@@ -38,6 +38,7 @@ SYMBOLS = [
     "bls_g1_batch_normalization_dev", "bls_g2_batch_normalization_dev", "bls_imad_peak",
     "bls_g1_wnaf_fixed_base_batch", "bls_g2_wnaf_fixed_base_batch", "bls_g1_wnaf_table", "bls_g2_wnaf_table",
     "bls_fq12_pow_batch", "bls_fq12_pow_dev", "bls_fr_op_batch",
+    "bls_g1_point_from_x_batch", "bls_g2_point_from_x_batch", "bls_g1_scale_by_cofactor_batch", "bls_g2_scale_by_cofactor_batch",
     "bls_g1_decode_batch", "bls_g2_decode_batch", "bls_g1_encode_batch", "bls_g2_encode_batch",
     "bls_g1_wnaf_table_dev", "bls_g2_wnaf_table_dev", "bls_g1_wnaf_fixed_base_dev", "bls_g2_wnaf_fixed_base_dev",
 ]
@@ -112,6 +113,10 @@ def load():
         "bls_g1_encode_batch": [vp, vp, ci, vp, sz],
         "bls_g2_encode_batch": [vp, vp, ci, vp, sz],
         "bls_fr_op_batch": [vp, ci, vp, vp, vp, vp, sz],
+        "bls_g1_point_from_x_batch": [vp, vp, vp, vp, vp, sz],
+        "bls_g2_point_from_x_batch": [vp, vp, vp, vp, vp, sz],
+        "bls_g1_scale_by_cofactor_batch": [vp, vp, vp, sz],
+        "bls_g2_scale_by_cofactor_batch": [vp, vp, vp, sz],
         "bls_fq12_pow_batch": [vp, vp, vp, vp, sz],
         "bls_fq12_pow_dev": [vp, vp, vp, vp, sz, vp],
         "bls_g2_prepare_dev": [vp, vp, vp, sz, vp],
@@ -369,6 +374,23 @@ class Context:
         return out, ok
 
     # ------------------------------------------------------------------ device pointers
+    def point_from_x(self, g2, x, greatest):
+        """$affine::get_point_from_x for n x-coordinates (Montgomery limbs) -> (affine rows, is_some)."""
+        x = _arr(x, W_FQ2 if g2 else W_FQ, "x")
+        gr = np.ascontiguousarray(greatest, dtype=np.uint8)
+        out = np.zeros((x.shape[0], W_G2A if g2 else W_G1A), dtype=np.uint64)
+        ok = np.zeros(x.shape[0], dtype=np.uint8)
+        fn = self._lib.bls_g2_point_from_x_batch if g2 else self._lib.bls_g1_point_from_x_batch
+        self._check(fn(self._ctx, _p(x), _p(gr), _p(out), _p(ok), x.shape[0]))
+        return out, ok
+
+    def scale_by_cofactor(self, g2, affine):
+        affine = _arr(affine, W_G2A if g2 else W_G1A, "affine")
+        out = np.zeros((affine.shape[0], W_G2 if g2 else W_G1), dtype=np.uint64)
+        fn = self._lib.bls_g2_scale_by_cofactor_batch if g2 else self._lib.bls_g1_scale_by_cofactor_batch
+        self._check(fn(self._ctx, _p(affine), _p(out), affine.shape[0]))
+        return out
+
     def fr_op(self, op, a, b=None):
         """Fr field operation (Montgomery-form (n,4) arrays; from_repr/into_repr convert) -> (values, ok)."""
         a = _arr(a, W_FR, "a")

@@ -152,6 +152,20 @@ template <class F> __device__ __forceinline__ bool is_in_correct_subgroup(const 
   return pt_is_zero(j);
 }
 
+// $affine::mul_bits with the cofactor (ec.rs:86-94, 871-875, 1564-1578): MSB-first over ALL bits of the limb array,
+// doubling a (still infinite) accumulator included, mixed additions -- the second half of G::rand (ec.rs:199-214).
+__device__ const uint32_t BLS_G1_COFACTOR[4] = {0x0000aaabu, 0x8c00aaabu, 0x5555e156u, 0x396c8c00u};
+__device__ const uint32_t BLS_G2_COFACTOR[16] = {0x1c7238e5u, 0xcf1c38e3u, 0x786f0c70u, 0x1616ec6eu, 0x3a6691aeu, 0x21537e29u, 0x4d9e82efu, 0xa628f1cbu,
+                                                 0x2e5a7ddfu, 0xa68a205bu, 0x47085abau, 0xcd91de45u, 0x2876a202u, 0x091d5079u, 0x5414e7f1u, 0x05d543a9u};
+template <class F> __device__ __forceinline__ void scale_by_cofactor(Jac<F>& res, const Aff<F>& p, const uint32_t* cof, int words) {
+  pt_set_zero(res);
+#pragma unroll 1
+  for (int i = 32 * words - 1; i >= 0; i--) {
+    pt_double(res);
+    if ((cof[i >> 5] >> (i & 31)) & 1u) pt_add_mixed(res, p);
+  }
+}
+
 // field-generic byte I/O: one "coordinate" is 48 bytes for Fq, 96 for Fq2 (c1 first: ec.rs:1371-1374)
 struct CoordLoad { bool ok; int bad_index; };
 __device__ __forceinline__ void f_load_be(Fp& out, const uint8_t* b, uint8_t mask, int coord, CoordLoad& st) {

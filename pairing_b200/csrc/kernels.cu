@@ -442,6 +442,30 @@ __global__ void __launch_bounds__(128) k_encode(const uint64_t* in, int compress
   encode_point(bytes + size * i, p, compressed != 0);
 }
 
+// $affine::get_point_from_x (ec.rs:102-123) and scale_by_cofactor: G::rand with the randomness supplied by the caller
+template <class F>
+__global__ void __launch_bounds__(128) k_point_from_x(const uint64_t* x, const uint8_t* greatest, uint64_t* out, uint8_t* is_some, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int AW = 2 * FW<F>::W + 1;
+  F xv; ld_F(xv, x + (size_t)FW<F>::W * i);
+  Aff<F> p;
+  const bool ok = get_point_from_x(p, xv, greatest[i] != 0);
+  if (!ok) { f_set_zero(p.x); f_set_one(p.y); p.inf = true; }
+  st_aff(out + (size_t)AW * i, p);
+  is_some[i] = ok;
+}
+template <class F, bool IS_G2>
+__global__ void __launch_bounds__(128) k_scale_by_cofactor(const uint64_t* in, uint64_t* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int AW = 2 * FW<F>::W + 1, PW = 3 * FW<F>::W;
+  Aff<F> p; ld_aff(p, in + (size_t)AW * i);
+  Jac<F> r;
+  scale_by_cofactor(r, p, IS_G2 ? BLS_G2_COFACTOR : BLS_G1_COFACTOR, IS_G2 ? 16 : 4);
+  st_jac(out + (size_t)PW * i, r);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Integer-multiply peak microbenchmarks (roofline denominator)
 // ------------------------------------------------------------------------------------------------
@@ -924,6 +948,45 @@ int bls_g1_decode_batch(bls_ctx* ctx, const uint8_t* bytes, int compressed, int 
 int bls_g2_decode_batch(bls_ctx* ctx, const uint8_t* bytes, int compressed, int checked, bls_g2_affine* out, uint8_t* status, size_t n) { return codec_host(ctx, 2, true, bytes, compressed, checked, out, status, n); }
 int bls_g1_encode_batch(bls_ctx* ctx, const bls_g1_affine* in, int compressed, uint8_t* bytes, size_t n) { return codec_host(ctx, 1, false, in, compressed, 0, bytes, nullptr, n); }
 int bls_g2_encode_batch(bls_ctx* ctx, const bls_g2_affine* in, int compressed, uint8_t* bytes, size_t n) { return codec_host(ctx, 2, false, in, compressed, 0, bytes, nullptr, n); }
+
+static int from_x_host(bls_ctx* ctx, int degree, const void* x, const uint8_t* greatest, void* out, uint8_t* is_some, size_t n) {
+  if (!ctx || (n && (!x || !greatest || !out || !is_some))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  const size_t xb = degree == 2 ? sizeof(bls_fq2) : sizeof(bls_fq);
+  const size_t ab = degree == 2 ? sizeof(bls_g2_affine) : sizeof(bls_g1_affine);
+  H2D(dx, x, n * xb);
+  H2D(dg, greatest, n);
+  DALLOC(dout, n * ab);
+  DALLOC(dok, n);
+  if (degree == 2) k_point_from_x<Fp2><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)dx.p, (const uint8_t*)dg.p, (uint64_t*)dout.p, (uint8_t*)dok.p, n);
+  else k_point_from_x<Fp><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)dx.p, (const uint8_t*)dg.p, (uint64_t*)dout.p, (uint8_t*)dok.p, n);
+  LAUNCH_CHECK();
+  D2H(out, dout, n * ab);
+  D2H(is_some, dok, n);
+  SYNC();
+  return BLS_OK;
+}
+int bls_g1_point_from_x_batch(bls_ctx* ctx, const bls_fq* x, const uint8_t* greatest, bls_g1_affine* out, uint8_t* is_some, size_t n) { return from_x_host(ctx, 1, x, greatest, out, is_some, n); }
+int bls_g2_point_from_x_batch(bls_ctx* ctx, const bls_fq2* x, const uint8_t* greatest, bls_g2_affine* out, uint8_t* is_some, size_t n) { return from_x_host(ctx, 2, x, greatest, out, is_some, n); }
+
+static int cofactor_host(bls_ctx* ctx, int degree, const void* in, void* out, size_t n) {
+  if (!ctx || (n && (!in || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  const size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
+  const size_t ab = degree == 2 ? sizeof(bls_g2_affine) : sizeof(bls_g1_affine);
+  H2D(din, in, n * ab);
+  DALLOC(dout, n * pb);
+  if (degree == 2) k_scale_by_cofactor<Fp2, true><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)din.p, (uint64_t*)dout.p, n);
+  else k_scale_by_cofactor<Fp, false><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)din.p, (uint64_t*)dout.p, n);
+  LAUNCH_CHECK();
+  D2H(out, dout, n * pb);
+  SYNC();
+  return BLS_OK;
+}
+int bls_g1_scale_by_cofactor_batch(bls_ctx* ctx, const bls_g1_affine* in, bls_g1* out, size_t n) { return cofactor_host(ctx, 1, in, out, n); }
+int bls_g2_scale_by_cofactor_batch(bls_ctx* ctx, const bls_g2_affine* in, bls_g2* out, size_t n) { return cofactor_host(ctx, 2, in, out, n); }
 
 static int bn_host(bls_ctx* ctx, int degree, void* inout, size_t n) {
   if (!ctx || (n && !inout)) return BLS_ERR_INVALID_ARGUMENT;

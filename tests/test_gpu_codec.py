@@ -112,3 +112,37 @@ def test_encode_decode_round_trip_random(ctx, g2):
     e2 = np.frombuffer(ctx.encode(g2, neg, True), dtype=np.uint8).reshape(n, -1)
     live = aff[:, -1] == 0
     assert np.array_equal(e1[live][:, 1:], e2[live][:, 1:]) and np.all((e1[live][:, 0] ^ e2[live][:, 0]) == 0x20)
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_point_from_x_and_scale_by_cofactor(ctx, g2):
+    """G::rand without the generator (ec.rs:199-214): get_point_from_x for random and small x (some have no root), then
+    scale_by_cofactor -- the Jacobian triple of the reference's mul_bits -- and the result lies in the r-order subgroup."""
+    import datagen as dg
+    n = 24
+    xs = [(v, 0) if g2 else v for v in range(8)]
+    rnd = dg.rand_fq(2 * n, 123)
+    for i in range(n):
+        a, b = m.from_limbs64(rnd[2 * i]) % m.Q, m.from_limbs64(rnd[2 * i + 1]) % m.Q
+        xs.append((a, b) if g2 else a)
+    greatest = [i & 1 for i in range(len(xs))]
+    rows = np.zeros((len(xs), 12 if g2 else 6), dtype=np.uint64)
+    for i, x in enumerate(xs):
+        vals = [x[0], x[1]] if g2 else [x]
+        for j, v in enumerate(vals):
+            rows[i, 6 * j:6 * j + 6] = np.array(m.limbs64(m.to_mont(v)), dtype=np.uint64)
+    aff, ok = ctx.point_from_x(g2, rows, greatest)
+    want = [m.get_point_from_x(x, bool(g), g2) for x, g in zip(xs, greatest)]
+    assert ok.tolist() == [int(w is not None) for w in want] and 0 < ok.sum() < len(xs)
+    good = [i for i, w in enumerate(want) if w is not None]
+    assert np.array_equal(aff[good], _aff_rows([want[i] for i in good], g2))
+    scaled = ctx.scale_by_cofactor(g2, aff[good])
+    for row, i in zip(scaled, good[:6]):                       # the model is pure Python: a few elements
+        assert row.tobytes() == m.to_bytes(m.scale_by_cofactor(want[i], g2))
+    # every scaled point is in the subgroup: checked decoding of its encoding succeeds
+    saff = (ctx.g2_into_affine if g2 else ctx.g1_into_affine)(scaled)
+    back, status = ctx.decode(g2, ctx.encode(g2, saff, True), True, checked=True)
+    assert not status.any() and np.array_equal(back, saff)
+    # ... while the unscaled points are (almost surely) not
+    _, st0 = ctx.decode(g2, ctx.encode(g2, aff[good], True), True, checked=True)
+    assert (st0 == m.DEC_NOT_IN_SUBGROUP).sum() >= len(good) - 1
