@@ -190,7 +190,10 @@ static __device__ __noinline__ void p12_sqr(P12& r, const P12& a) {
   p6_mul_by_nonresidue(ab, ab);
   p6_sub(r.c0, c0, ab);
 }
-// Granger-Scott cyclotomic squaring (see fp12_cyclotomic_sqr in tower.cuh)
+// Squaring for elements of the cyclotomic subgroup (Granger-Scott, "Faster squaring in the cyclotomic subgroup of sixth
+// degree extensions"): three Fq4 squarings, 18 M instead of the 36 M of the generic fq12.rs:99-114.  Only used inside
+// exp_by_x, whose operand lies in the cyclotomic subgroup after the easy part of the final exponentiation, where it
+// returns the same field value as `square`.  z' = 3t - 2z for the "real" parts, 3t + 2z for the "imaginary" ones.
 __device__ __forceinline__ void p4_sqr(P2& t0, P2& t1, const P2& a, const P2& b) {
   P2 tmp = p2_mul(a, b);
   P2 s = p2_mul(p2_add(a, b), p2_add(p2_mul_by_nonresidue(b), a));

@@ -191,32 +191,6 @@ static __device__ __noinline__ void fp12_sqr(Fp12& r, const Fp12& a) {
   fp6_mul_by_nonresidue(ab, ab);
   fp6_sub(r.c0, c0, ab);
 }
-// Squaring for elements of the cyclotomic subgroup (Granger-Scott, "Faster squaring in the cyclotomic
-// subgroup of sixth degree extensions"): three Fq4 squarings, 18 M instead of the 36 M of the generic
-// fq12.rs:99-114.  Only used inside exp_by_x, whose operand lies in the cyclotomic subgroup after the
-// easy part of the final exponentiation, where it returns the same field value as `square`.
-__device__ __forceinline__ void fp4_sqr(Fp2& t0, Fp2& t1, const Fp2& a, const Fp2& b) {
-  Fp2 tmp = fp2_mul(a, b);
-  Fp2 s = fp2_mul(fp2_add(a, b), fp2_add(fp2_mul_by_nonresidue(b), a));
-  t0 = fp2_sub(fp2_sub(s, tmp), fp2_mul_by_nonresidue(tmp));   // a^2 + xi b^2
-  t1 = fp2_dbl(tmp);                                           // 2ab
-}
-static __device__ __noinline__ void fp12_cyclotomic_sqr(Fp12& r, const Fp12& f) {
-  Fp2 t0, t1, t2, t3, t4, t5;
-  fp4_sqr(t0, t1, f.c0.c0, f.c1.c1);
-  fp4_sqr(t2, t3, f.c1.c0, f.c0.c2);
-  fp4_sqr(t4, t5, f.c0.c1, f.c1.c2);
-  // z' = 3t - 2z for the "real" parts, 3t + 2z for the "imaginary" ones
-  Fp2 z0 = fp2_sub(t0, f.c0.c0); z0 = fp2_add(fp2_dbl(z0), t0);
-  Fp2 z1 = fp2_add(t1, f.c1.c1); z1 = fp2_add(fp2_dbl(z1), t1);
-  Fp2 x5 = fp2_mul_by_nonresidue(t5);
-  Fp2 z2 = fp2_add(x5, f.c1.c0); z2 = fp2_add(fp2_dbl(z2), x5);
-  Fp2 z3 = fp2_sub(t4, f.c0.c2); z3 = fp2_add(fp2_dbl(z3), t4);
-  Fp2 z4 = fp2_sub(t2, f.c0.c1); z4 = fp2_add(fp2_dbl(z4), t2);
-  Fp2 z5 = fp2_add(t3, f.c1.c2); z5 = fp2_add(fp2_dbl(z5), t3);
-  r.c0.c0 = z0; r.c0.c1 = z4; r.c0.c2 = z3;
-  r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
-}
 // fq12.rs:34-48 (in place on f)
 static __device__ __noinline__ void fp12_mul_by_014(Fp12& f, const Fp2& c0, const Fp2& c1, const Fp2& c4) {
   Fp6 aa, bb, s;
