@@ -48,13 +48,13 @@ __device__ __forceinline__ bool p2_is_zero(const P2& a) {
   return z && __shfl_xor_sync(0xffffffffu, (int)z, 1);
 }
 // x (1 + u) = (c0 - c1) + (c0 + c1) u   (fq2.rs:41-45)
-static __device__ __noinline__ P2 p2_mul_by_nonresidue(P2 a) {
+__device__ __forceinline__ P2 p2_mul_by_nonresidue(P2 a) {
   Fp oth = pair_xchg(a.v);
   // lane 0: c0 - c1 = own + (2q - oth);  lane 1: c1 + c0 = own + oth   (one folded addition instead of add, sub, select)
   return P2{fp_add(a.v, fp_select(pair_c() == 0, fp_neg(oth), oth))};
 }
 // fq2.rs:123-136: c0 = a0 b0 - a1 b1, c1 = a0 b1 + a1 b0, one lazily reduced dual product per lane
-static __device__ __noinline__ P2 p2_mul(P2 a, P2 b) {
+__device__ __forceinline__ P2 p2_mul(P2 a, P2 b) {
   Fp ao = pair_xchg(a.v), bo = pair_xchg(b.v);
   bool c0 = pair_c() == 0;
   // lane 0: a0 * b0 + (-a1) * b1        lane 1: a0 * b1 + a1 * b0   (X * b_own + Y * b_oth)
@@ -63,7 +63,7 @@ static __device__ __noinline__ P2 p2_mul(P2 a, P2 b) {
   return P2{fp_mul2(x, b.v, y, bo)};
 }
 // fq2.rs:87-101: c0 = (a0 + a1)(a0 - a1), c1 = 2 a0 a1
-static __device__ __noinline__ P2 p2_sqr(P2 a) {
+__device__ __forceinline__ P2 p2_sqr(P2 a) {
   Fp oth = pair_xchg(a.v);
   bool c0 = pair_c() == 0;
   Fp u = fp_add(fp_select(c0, a.v, oth), oth);           // lane 0: a0 + a1, lane 1: a0 + a0
@@ -122,14 +122,14 @@ static __device__ __noinline__ void p6_sqr(P6& r, const P6& a) {
   r.c2 = p2_sub(p2_sub(p2_add(p2_add(s1, s2), s3), s0), s4);
 }
 // fq6.rs:40-66
-static __device__ __noinline__ void p6_mul_by_1(P6& r, const P6& a, const P2& c1) {
+__device__ __forceinline__ void p6_mul_by_1(P6& r, const P6& a, const P2& c1) {
   P2 bb = p2_mul(a.c1, c1);
   P2 t1 = p2_mul_by_nonresidue(p2_sub(p2_mul(c1, p2_add(a.c1, a.c2)), bb));
   P2 t2 = p2_sub(p2_mul(c1, p2_add(a.c0, a.c1)), bb);
   r.c0 = t1; r.c1 = t2; r.c2 = bb;
 }
 // fq6.rs:68-109
-static __device__ __noinline__ void p6_mul_by_01(P6& r, const P6& a, const P2& c0, const P2& c1) {
+__device__ __forceinline__ void p6_mul_by_01(P6& r, const P6& a, const P2& c0, const P2& c1) {
   P2 aa = p2_mul(a.c0, c0);
   P2 bb = p2_mul(a.c1, c1);
   P2 t1 = p2_add(p2_mul_by_nonresidue(p2_sub(p2_mul(c1, p2_add(a.c1, a.c2)), bb)), aa);
@@ -178,7 +178,7 @@ static __device__ __noinline__ void p12_mul(P12& r, const P12& a, const P12& b) 
   p6_add(r.c0, bb, aa);
 }
 // fq12.rs:99-114
-static __device__ __noinline__ void p12_sqr(P12& r, const P12& a) {
+__device__ __forceinline__ void p12_sqr(P12& r, const P12& a) {
   P6 ab, c0c1, c0;
   p6_mul(ab, a.c0, a.c1);
   p6_add(c0c1, a.c0, a.c1);
