@@ -421,7 +421,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "imad", "achieved": achieved / 1e12, "peak": peak_macs / 1e12, "unit": "TMAC32/s",
                      "frac": achieved / peak_macs, "traffic": traffic,
-                     "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of profiles/r1_pair_miller.md; mostly local-memory (spill) write-back, ~52 GB/s",
+                     "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of profiles/r1_pair_miller.md; mostly local-memory write-back, ~49 GB/s",
                      "kernel": "k_pair_miller<true> (fused Miller loop + final exponentiation on lane pairs, one launch per step)",
                      "kernel_ms": kernel_ms, "mac32_per_pairing": MAC32_PER_PAIRING,
                      "peak_source": "chain of dependent IMAD.WIDE.U32 (bls_imad_peak variant 0, SASS-checked by tests/test_abi.py) measured in this run: one 32x32->64 multiply per 4 cycles per SM sub-partition; MEASURED_PEAKS.json has no integer figure",
