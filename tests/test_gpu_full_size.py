@@ -72,6 +72,8 @@ def test_pairing_full_batch(eng, data):
     assert bool(ok.all()) and torch.equal(gt, fe)
     idx = np.r_[np.arange(0, N_PAIR, N_PAIR // 128), 5, 9, N_PAIR - 1]
     assert np.array_equal(_np(gt)[idx], o.pairing(_np(pa)[idx], _np(qa)[idx], TH))
+    head = slice(0, 8192)                             # and every output of the first 2^13 pairs, bit for bit
+    assert np.array_equal(_np(gt)[head], o.pairing(_np(pa)[head], _np(qa)[head], TH))
     one = np.zeros(72, dtype=np.uint64); one[:6] = _np(data[2])[0, 12:18]
     assert np.array_equal(_np(gt)[5], one) and np.array_equal(_np(gt)[9], one)
     # multi-Miller over the whole batch == product of the single Miller values (two different kernels)
