@@ -165,32 +165,28 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_final_exp(
   }
 }
 
-// Field::pow on Fq12 with an FrRepr exponent (lib.rs:306-324; GT exponentiation, tests/engine.rs:121):
-// MSB-first square-and-multiply.  The exponent differs per lane pair, so the loop is branch-free over all
-// 256 bits (every lane has to reach every shuffle): squarings and products are computed for the whole warp
-// and committed per lane pair.  Generic squaring (the input need not be in the cyclotomic subgroup).
+// Field::pow on Fq12 with an FrRepr exponent (lib.rs:306-324; GT exponentiation, tests/engine.rs:121).  The reference
+// is MSB-first square-and-multiply; the value of a power does not depend on the addition chain, so this is a 4-bit
+// fixed window: 252 squarings + 64 table products, and -- the exponent differing per lane pair while every lane has to
+// reach every shuffle -- completely uniform control flow (a zero window multiplies by table[0] = one).  Generic
+// squaring: the input need not be in the cyclotomic subgroup.
 __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_fq12_pow(const uint64_t* in, const uint64_t* k, uint64_t* out, size_t n) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = t >> 1;
   const bool active = i < n;
   if (!active) i = n - 1;
-  P12 a, res, tmp;
-  ld_p12(a, in + FQ12_W * i);
-  Scalar s = ld_scalar(k + 4 * i);
-  p12_one(res);
-  bool found = false;
+  P12 tbl[16];
+  p12_one(tbl[0]);
+  ld_p12(tbl[1], in + FQ12_W * i);
 #pragma unroll 1
-  for (int b = 255; b >= 0; b--) {
-    const bool bit = (s.v[b >> 5] >> (b & 31)) & 1u;
-    if (__any_sync(0xffffffffu, found)) {
-      p12_sqr(tmp, res);
-      p12_select(res, found, tmp, res);
-    }
-    found |= bit;
-    if (__any_sync(0xffffffffu, bit)) {
-      p12_mul(tmp, res, a);
-      p12_select(res, bit, tmp, res);
-    }
+  for (int e = 2; e < 16; e++) p12_mul(tbl[e], tbl[e - 1], tbl[1]);
+  const Scalar s = ld_scalar(k + 4 * i);
+  P12 res = tbl[(s.v[7] >> 28) & 0xf];
+#pragma unroll 1
+  for (int w = 62; w >= 0; w--) {
+    p12_sqr(res, res); p12_sqr(res, res); p12_sqr(res, res); p12_sqr(res, res);
+    const uint32_t nib = (s.v[w >> 3] >> ((w & 7) * 4)) & 0xf;
+    p12_mul(res, res, tbl[nib]);
   }
   if (active) st_p12(out + FQ12_W * i, res);
 }
