@@ -74,6 +74,11 @@ int bls_g2_prepare_batch(bls_ctx*, const bls_g2_affine* q, bls_g2_prepared* out,
 int bls_miller_loop_batch(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n);
 /* same, from already prepared G2 coefficients (the reference's actual miller_loop signature) */
 int bls_miller_loop_prepared_batch(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q, bls_fq12* out, size_t n);
+/* n independent Miller loops / pairings e(P_i, Q) against ONE prepared G2 point: the reference's
+ * `let q = Q.prepare(); for p_i { Engine::miller_loop(&[(&p_i.prepare(), &q)]) }` (the reason G2Prepared exists,
+ * ec.rs:1615-1619).  The coefficients are staged once per block in shared memory by a TMA bulk copy. */
+int bls_miller_loop_shared_q_batch(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q1, bls_fq12* out, size_t n);
+int bls_pairing_shared_q_batch(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q1, bls_fq12* out, size_t n);
 /* ONE Engine::miller_loop over n pairs: the product of the n Miller values (mod.rs:80-95). */
 int bls_multi_miller_loop(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1);
 int bls_multi_miller_loop_prepared(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q, size_t n, bls_fq12* out1);
@@ -175,6 +180,8 @@ int bls_miller_loop_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q
 int bls_miller_loop_prepared_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q, bls_fq12* out, size_t n, void* stream);
 int bls_final_exponentiation_dev(bls_ctx*, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n, void* stream);
 int bls_pairing_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream);
+/* q1: ONE prepared point in device memory, 16-byte aligned; final_exp != 0 adds the final exponentiation */
+int bls_miller_loop_shared_q_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q1, bls_fq12* out, size_t n, int final_exp, void* stream);
 int bls_fq12_pow_dev(bls_ctx*, const bls_fq12* a, const bls_fr_repr* k, bls_fq12* out, size_t n, void* stream);
 /* scratch: bls_multi_miller_scratch_bytes(ctx, n) bytes */
 size_t bls_multi_miller_scratch_bytes(const bls_ctx*, size_t n);

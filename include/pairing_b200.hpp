@@ -131,6 +131,17 @@ struct Bls12 {
     g.check(bls_pairing_batch(g.ctx(), p.data(), q.data(), out.data(), p.size()));
     return out;
   }
+  // e(p_i, q) for every p_i against ONE prepared q: `let q = Q.prepare(); for p in ps { pairing ... }`
+  static std::vector<Fq12> pairing_shared_q(Gpu& g, const std::vector<G1AffinePoint>& p, const G2PreparedPoint& q) {
+    std::vector<Fq12> out(p.size());
+    g.check(bls_pairing_shared_q_batch(g.ctx(), p.data(), &q, out.data(), p.size()));
+    return out;
+  }
+  static std::vector<Fq12> miller_loop_shared_q(Gpu& g, const std::vector<G1PreparedPoint>& p, const G2PreparedPoint& q) {
+    std::vector<Fq12> out(p.size());
+    g.check(bls_miller_loop_shared_q_batch(g.ctx(), p.data(), &q, out.data(), p.size()));
+    return out;
+  }
   // Field::pow on Fqk with a scalar-field exponent (lib.rs:306-324)
   static std::vector<Fq12> pow(Gpu& g, const std::vector<Fq12>& a, const std::vector<FrRepr>& k) {
     if (a.size() != k.size()) throw Error(BLS_ERR_INVALID_ARGUMENT, "pow: length mismatch");

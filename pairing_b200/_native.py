@@ -38,6 +38,7 @@ SYMBOLS = [
     "bls_g1_batch_normalization_dev", "bls_g2_batch_normalization_dev", "bls_imad_peak",
     "bls_g1_wnaf_fixed_base_batch", "bls_g2_wnaf_fixed_base_batch", "bls_g1_wnaf_table", "bls_g2_wnaf_table",
     "bls_fq12_pow_batch", "bls_fq12_pow_dev", "bls_fr_op_batch",
+    "bls_miller_loop_shared_q_batch", "bls_pairing_shared_q_batch", "bls_miller_loop_shared_q_dev",
     "bls_g1_point_from_x_batch", "bls_g2_point_from_x_batch", "bls_g1_scale_by_cofactor_batch", "bls_g2_scale_by_cofactor_batch",
     "bls_g1_decode_batch", "bls_g2_decode_batch", "bls_g1_encode_batch", "bls_g2_encode_batch",
     "bls_g1_wnaf_table_dev", "bls_g2_wnaf_table_dev", "bls_g1_wnaf_fixed_base_dev", "bls_g2_wnaf_fixed_base_dev",
@@ -113,6 +114,9 @@ def load():
         "bls_g1_encode_batch": [vp, vp, ci, vp, sz],
         "bls_g2_encode_batch": [vp, vp, ci, vp, sz],
         "bls_fr_op_batch": [vp, ci, vp, vp, vp, vp, sz],
+        "bls_miller_loop_shared_q_batch": [vp, vp, vp, vp, sz],
+        "bls_pairing_shared_q_batch": [vp, vp, vp, vp, sz],
+        "bls_miller_loop_shared_q_dev": [vp, vp, vp, vp, sz, ci, vp],
         "bls_g1_point_from_x_batch": [vp, vp, vp, vp, vp, sz],
         "bls_g2_point_from_x_batch": [vp, vp, vp, vp, vp, sz],
         "bls_g1_scale_by_cofactor_batch": [vp, vp, vp, sz],
@@ -216,6 +220,21 @@ class Context:
 
     def pairing(self, p, q):
         return self._pq(self._lib.bls_pairing_batch, p, q, W_G2A)
+
+    def _shared_q(self, fn, p, q1):
+        p, q1 = _arr(p, W_G1A, "p"), _arr(q1, W_G2P, "q1")
+        if q1.shape[0] != 1:
+            raise ValueError("q1 must be ONE prepared G2 point")
+        out = np.zeros((p.shape[0], W_FQ12), dtype=np.uint64)
+        self._check(fn(self._ctx, _p(p), _p(q1), _p(out), p.shape[0]))
+        return out
+
+    def miller_loop_shared_q(self, p, q1):
+        """n Miller loops e(P_i, Q) against one prepared Q."""
+        return self._shared_q(self._lib.bls_miller_loop_shared_q_batch, p, q1)
+
+    def pairing_shared_q(self, p, q1):
+        return self._shared_q(self._lib.bls_pairing_shared_q_batch, p, q1)
 
     def _multi(self, fn, p, q, wq):
         p, q = _arr(p, W_G1A, "p"), _arr(q, wq, "q")

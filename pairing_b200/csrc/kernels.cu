@@ -788,6 +788,21 @@ int bls_miller_loop_prepared_batch(bls_ctx* ctx, const bls_g1_affine* p, const b
   return BLS_OK;
 }
 
+static int shared_q_host(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q1, bls_fq12* out, size_t n, int final_exp) {
+  if (!ctx || !q1 || (n && (!p || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  H2D(dp, p, n * sizeof(*p));
+  H2D(dq, q1, sizeof(*q1));
+  DALLOC(dout, n * sizeof(*out));
+  TRY(bls_miller_loop_shared_q_dev(ctx, (const bls_g1_affine*)dp.p, (const bls_g2_prepared*)dq.p, (bls_fq12*)dout.p, n, final_exp, nullptr));
+  D2H(out, dout, n * sizeof(*out));
+  SYNC();
+  return BLS_OK;
+}
+int bls_miller_loop_shared_q_batch(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q1, bls_fq12* out, size_t n) { return shared_q_host(ctx, p, q1, out, n, 0); }
+int bls_pairing_shared_q_batch(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q1, bls_fq12* out, size_t n) { return shared_q_host(ctx, p, q1, out, n, 1); }
+
 int bls_multi_miller_loop(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1) {
   if (!ctx || !out1 || (n && (!p || !q))) return BLS_ERR_INVALID_ARGUMENT;
   CK(cudaSetDevice(ctx->device));

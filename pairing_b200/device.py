@@ -69,6 +69,15 @@ class DeviceEngine:
         self.ctx.call_dev("bls_miller_loop_prepared_dev", p.data_ptr(), qp.data_ptr(), out.data_ptr(), n, self._stream())
         return out
 
+    def pairing_shared_q(self, p, q1_prepared, out=None, final_exp=True):
+        """e(P_i, Q) for every P_i against ONE prepared Q ((1, 2449) tensor): coefficients staged in shared memory by TMA."""
+        _check(p, nat.W_G1A, "p"); _check(q1_prepared, nat.W_G2P, "q1_prepared")
+        n = p.shape[0]
+        if out is None:
+            out = torch.empty((n, nat.W_FQ12), dtype=torch.int64, device=self.device)
+        self.ctx.call_dev("bls_miller_loop_shared_q_dev", p.data_ptr(), q1_prepared.data_ptr(), out.data_ptr(), n, 1 if final_exp else 0, self._stream())
+        return out
+
     def final_exponentiation(self, f, out=None):
         _check(f, nat.W_FQ12, "f")
         n = f.shape[0]

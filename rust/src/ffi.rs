@@ -26,6 +26,8 @@ extern "C" {
     pub fn bls_g2_prepare_batch(ctx: *mut bls_ctx, q: *const bls_g2_affine, out: *mut bls_g2_prepared, n: usize) -> c_int;
     pub fn bls_miller_loop_batch(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_affine, out: *mut bls_fq12, n: usize) -> c_int;
     pub fn bls_miller_loop_prepared_batch(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_prepared, out: *mut bls_fq12, n: usize) -> c_int;
+    pub fn bls_miller_loop_shared_q_batch(ctx: *mut bls_ctx, p: *const bls_g1_affine, q1: *const bls_g2_prepared, out: *mut bls_fq12, n: usize) -> c_int;
+    pub fn bls_pairing_shared_q_batch(ctx: *mut bls_ctx, p: *const bls_g1_affine, q1: *const bls_g2_prepared, out: *mut bls_fq12, n: usize) -> c_int;
     pub fn bls_multi_miller_loop(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_affine, n: usize, out1: *mut bls_fq12) -> c_int;
     pub fn bls_multi_miller_loop_prepared(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_prepared, n: usize, out1: *mut bls_fq12) -> c_int;
     pub fn bls_final_exponentiation_batch(ctx: *mut bls_ctx, input: *const bls_fq12, out: *mut bls_fq12, is_some: *mut u8, n: usize) -> c_int;

@@ -122,6 +122,11 @@ static void random_miller_loop_tests(Gpu& g) {
     auto dbl = Bls12::final_exponentiation(g, Bls12::miller_loop(g, {aa[i], ca[i]}, {pb[i], pd[i]}));
     CHECK(dbl.has_value() && *dbl == abcd);
   }
+  // many G1 points against one prepared G2 point (the use G2Prepared exists for)
+  {
+    std::vector<G2AffinePoint> rep(n, ba[3]);
+    CHECK(same(Bls12::pairing_shared_q(g, aa, pb[3]), Bls12::pairing(g, aa, rep)));
+  }
   // one multi-Miller loop over all 2n pairs == product of everything
   std::vector<G1AffinePoint> allp(aa); allp.insert(allp.end(), ca.begin(), ca.end());
   std::vector<G2AffinePoint> allq(ba); allq.insert(allq.end(), da.begin(), da.end());

@@ -308,3 +308,19 @@ def test_fr_ops(ctx, op):
         x = np.array([[0x6b7e9b8faeefc81a, 0xe30a8463f348ba42, 0xeff3cb67a8279c9c, 0x3d303651bd7c774d]], dtype=np.uint64)
         y = np.array([[0x13ae28e3bc35ebeb, 0xa10f4488075cae2c, 0x8160e95a853c3b5d, 0x5ae3f03b561a841d]], dtype=np.uint64)
         assert ctx.fr_op("mul", x, y)[0].tolist() == [[0x23717213ce710f71, 0xdbee1fe53a16e1af, 0xf565d3e1c2a48000, 0x4426507ee75df9d7]]
+
+
+def test_shared_q_miller_and_pairing(ctx):
+    """e(P_i, Q) against ONE prepared Q (coefficients staged in shared memory by a TMA bulk copy): the same values as the
+    per-pair kernels and as the oracle's literal miller_loop over the replicated G2Prepared; infinity on either side -> one."""
+    n = 333
+    p = dg.g1_affine_points(n, 95, infinity_at=(6,))
+    q = dg.g2_affine_points(2, 96, infinity_at=(1,))
+    qp = o.g2_prepare(q, TH)
+    for j in (0, 1):                                    # j == 1: Q at infinity
+        rep_q = np.repeat(q[j:j + 1], n, 0)
+        want_m = o.miller_loop_prepared(p, np.repeat(qp[j:j + 1], n, 0), TH)
+        eq(ctx.miller_loop_shared_q(p, qp[j:j + 1]), want_m)
+        eq(ctx.pairing_shared_q(p, qp[j:j + 1]), o.pairing(p, rep_q, TH))
+    eq(ctx.miller_loop_shared_q(p, ctx.g2_prepare(q[:1])), ctx.miller_loop(p, np.repeat(q[:1], n, 0)))
+    assert ctx.pairing_shared_q(p[:0], qp[:1]).shape == (0, 72)
