@@ -81,7 +81,42 @@ impl Gpu {
         for (dst, src) in v.iter_mut().zip(vv.iter()) { *dst = marshal::g1_back(src); }
         Ok(())
     }
-    // g2_wnaf_mul_batch, g2_batch_normalization, g2_prepare_batch, miller_loop_batch: same pattern.
+    /// `Wnaf::new().base(g, k.len()).scalar(k_i)` for every scalar: one shared window table (wnaf.rs:93-107, 169-178).
+    pub fn g1_wnaf_fixed_base(&self, base: &G1, k: &[FrRepr]) -> Result<Vec<G1>, GpuError> {
+        use pairing::CurveProjective;
+        let window = G1::recommended_wnaf_for_num_scalars(k.len()) as i32;
+        let b = marshal::g1(base);
+        let kk: Vec<bls_fr_repr> = k.iter().map(|r| bls_fr_repr { l: r.0 }).collect();
+        let mut out = vec![b; k.len()];
+        let ctx = self.ctx.lock().unwrap();
+        check(unsafe { bls_g1_wnaf_fixed_base_batch(*ctx, &b, window, kk.as_ptr(), out.as_mut_ptr(), kk.len()) }, *ctx)?;
+        Ok(out.iter().map(marshal::g1_back).collect())
+    }
+
+    /// `let q = Q.prepare(); ps.iter().map(|p| Bls12::pairing(p, Q))` with the one `G2Prepared` staged on the device.
+    pub fn pairing_shared_q(&self, p: &[G1Affine], q: &G2Affine) -> Result<Vec<Fq12>, GpuError> {
+        let pp: Vec<bls_g1_affine> = p.iter().map(marshal::g1_affine).collect();
+        let qq = marshal::g2_affine(q);
+        let mut prepared: Box<bls_g2_prepared> = Box::new(unsafe { std::mem::zeroed() });
+        let mut out = vec![marshal::FQ12_ZERO; p.len()];
+        let ctx = self.ctx.lock().unwrap();
+        check(unsafe { bls_g2_prepare_batch(*ctx, &qq, &mut *prepared, 1) }, *ctx)?;
+        check(unsafe { bls_pairing_shared_q_batch(*ctx, pp.as_ptr(), &*prepared, out.as_mut_ptr(), pp.len()) }, *ctx)?;
+        Ok(out.iter().map(marshal::fq12_back).collect())
+    }
+
+    /// `G1Compressed::into_affine` for every 48-byte encoding: `Err(code)` carries the reference's `GroupDecodingError`
+    /// as the status byte of include/pairing_b200.h (BLS_DEC_*).
+    pub fn g1_decode_compressed(&self, bytes: &[u8]) -> Result<Vec<Result<G1Affine, u8>>, GpuError> {
+        assert_eq!(bytes.len() % 48, 0);
+        let n = bytes.len() / 48;
+        let mut out = vec![bls_g1_affine { x: marshal::FQ_ZERO, y: marshal::FQ_ZERO, infinity: 0 }; n];
+        let mut status = vec![0u8; n];
+        let ctx = self.ctx.lock().unwrap();
+        check(unsafe { bls_g1_decode_batch(*ctx, bytes.as_ptr(), 1, 1, out.as_mut_ptr(), status.as_mut_ptr(), n) }, *ctx)?;
+        Ok(out.iter().zip(status).map(|(a, s)| if s == 0 { Ok(marshal::g1_affine_back(a)) } else { Err(s) }).collect())
+    }
+    // g2_wnaf_mul_batch, g2_batch_normalization, g2_prepare_batch, miller_loop_batch, the other encodings: same pattern.
 }
 
 impl Drop for Gpu {
@@ -118,6 +153,7 @@ mod marshal {
     pub fn fq12_back(x: &bls_fq12) -> Fq12 { Fq12 { c0: fq6_back(&x.c0), c1: fq6_back(&x.c1) } }
     pub fn g1_affine(p: &G1Affine) -> bls_g1_affine { bls_g1_affine { x: fq(&p.x), y: fq(&p.y), infinity: p.infinity as u64 } }
     pub fn g2_affine(p: &G2Affine) -> bls_g2_affine { bls_g2_affine { x: fq2(&p.x), y: fq2(&p.y), infinity: p.infinity as u64 } }
+    pub fn g1_affine_back(p: &bls_g1_affine) -> G1Affine { G1Affine { x: fq_back(&p.x), y: fq_back(&p.y), infinity: p.infinity != 0 } }
     pub fn g1(p: &G1) -> bls_g1 { bls_g1 { x: fq(&p.x), y: fq(&p.y), z: fq(&p.z) } }
     pub fn g1_back(p: &bls_g1) -> G1 { G1 { x: fq_back(&p.x), y: fq_back(&p.y), z: fq_back(&p.z) } }
 }
