@@ -268,6 +268,52 @@ template <class F, int K, class Tab, class D> __device__ __forceinline__ void pt
   }
 }
 
+// ---- warp-cooperative addition of a FIXED point, for the window table of the fixed-base mode (wnaf.rs:4-15) ----
+// table[i+1] = table[i] + 2g is a chain of 2^(w-1) DEPENDENT additions (each entry's Jacobian representative depends on the
+// previous one), so it cannot be spread over points; but inside one add-2007-bl there are up to three independent
+// products per level.  Lanes of one warp hold the same point; lane r (mod 3) computes product r of each level and the
+// results are broadcast by shuffles: 6 multiply levels instead of 16 sequential products.  z2^2 and z2^3 of the fixed
+// operand are computed once.  Same field values as pt_add_core, hence the same canonical triple.
+__device__ __forceinline__ Fp f_sel(bool a, const Fp& x, const Fp& y) {
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = a ? x.v[i] : y.v[i];
+  return r;
+}
+__device__ __forceinline__ Fp2 f_sel(bool a, const Fp2& x, const Fp2& y) { return Fp2{f_sel(a, x.c0, y.c0), f_sel(a, x.c1, y.c1)}; }
+__device__ __forceinline__ Fp f_bcast(const Fp& x, int src) {
+  Fp r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = __shfl_sync(0xffffffffu, x.v[i], src);
+  return r;
+}
+__device__ __forceinline__ Fp2 f_bcast(const Fp2& x, int src) { return Fp2{f_bcast(x.c0, src), f_bcast(x.c1, src)}; }
+template <class F> __device__ __forceinline__ F f_sel3(int role, const F& a, const F& b, const F& c) { return f_sel(role == 0, a, f_sel(role == 1, b, c)); }
+
+// s += o for a fixed o with z2z2 = o.z^2 and z2c = o.z^3; every lane of the warp holds the same s and o.
+template <class F> __device__ __forceinline__ void pt_add_fixed_coop(Jac<F>& s, const Jac<F>& o, const F& z2z2, const F& z2c) {
+  if (pt_is_zero(s) || pt_is_zero(o)) { pt_add(s, o); return; }          // warp-uniform: all lanes hold the same values
+  const int role = (threadIdx.x & 31) % 3;
+  F m = f_mul(f_sel3(role, s.z, s.x, s.y), f_sel3(role, s.z, z2z2, z2c));
+  const F z1z1 = f_bcast(m, 0), u1 = f_bcast(m, 1), s1 = f_bcast(m, 2);
+  const F zs = f_add(s.z, o.z);
+  m = f_mul(f_sel3(role, o.x, s.z, zs), f_sel3(role, z1z1, z1z1, zs));
+  const F u2 = f_bcast(m, 0), z1c = f_bcast(m, 1), zz = f_bcast(m, 2);
+  const F h = f_sub(u2, u1), h2 = f_dbl(h);
+  m = f_mul(f_sel(role == 0, o.y, h2), f_sel(role == 0, z1c, h2));
+  const F s2 = f_bcast(m, 0), i = f_bcast(m, 1);
+  const F sd = f_sub(s2, s1);
+  if (f_is_zero(h) && f_is_zero(sd)) { pt_double(s); return; }           // equal operands (ec.rs:394-396), warp-uniform
+  m = f_mul(f_sel3(role, h, u1, f_sub(f_sub(zz, z1z1), z2z2)), f_sel3(role, i, i, h));
+  const F j = f_bcast(m, 0), v = f_bcast(m, 1), z3 = f_bcast(m, 2);
+  const F r = f_dbl(sd);
+  m = f_mul(f_sel(role == 0, r, s1), f_sel(role == 0, r, j));
+  const F r2 = f_bcast(m, 0), s1j = f_bcast(m, 1);
+  s.x = f_sub(f_sub(f_sub(r2, j), v), v);
+  s.y = f_sub(f_mul(f_sub(v, s.x), r), f_dbl(s1j));
+  s.z = z3;
+}
+
 // double-and-add, ec.rs:534-553
 template <class F> __device__ __forceinline__ void pt_mul(Jac<F>& s, const Scalar& k) {
   Jac<F> res;

@@ -275,20 +275,21 @@ __global__ void __launch_bounds__(128, IS_G2 ? BLS_WNAF_MINB : BLS_WNAF_MINB + 1
 // Fixed-base mode, Wnaf::new().base(g, num_scalars) then .scalar(s_i) per scalar (wnaf.rs:93-107, 169-178):
 // ONE window table shared by all scalars, window 2..16 from recommended_wnaf_for_num_scalars.
 // k_wnaf_table builds it: table[i] = (2i+1) g by repeated projective additions of 2g -- a chain of 2^(w-1)
-// dependent additions (each entry's Jacobian representative depends on the previous one), so one thread.
+// dependent additions (each entry's Jacobian representative depends on the previous one): ONE warp, whose lanes split
+// the independent products inside each addition (curve.cuh: pt_add_fixed_coop).
 template <class F>
 __global__ void __launch_bounds__(32) k_wnaf_table(const uint64_t* base, uint64_t* table, int window) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const int PW = 3 * FW<F>::W;
   Jac<F> b, dbl;
   ld_jac(b, base);
   dbl = b;
   pt_double(dbl);
+  const F z2z2 = f_sqr(dbl.z), z2c = f_mul(dbl.z, z2z2);
   const int tsize = 1 << (window - 1);
 #pragma unroll 1
   for (int e = 0; e < tsize; e++) {
-    st_jac(table + (size_t)PW * e, b);
-    if (e + 1 < tsize) pt_add(b, dbl);
+    if (threadIdx.x == 0) st_jac(table + (size_t)PW * e, b);
+    if (e + 1 < tsize) pt_add_fixed_coop(b, dbl, z2z2, z2c);
   }
 }
 template <class F, int K>
