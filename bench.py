@@ -317,6 +317,16 @@ def run_ours(args):
             d.update(kw)
             return d
 
+        # configs[0]: a single pairing e(P, Q) (latency of a batch of one) and the crate's bench_pairing_full shape (1000 pairings)
+        one_out = torch.empty((1, 72), dtype=torch.int64, device=eng.device)
+        eng.pairing(pa[:1].contiguous(), qa[:1].contiguous(), one_out)
+        ms_one, _ = timed(lambda: eng.pairing(pa[:1].contiguous(), qa[:1].contiguous(), one_out))
+        k_out = torch.empty((1000, 72), dtype=torch.int64, device=eng.device)
+        eng.pairing(pa[:1000].contiguous(), qa[:1000].contiguous(), k_out)
+        ms_k, _ = timed(lambda: eng.pairing(pa[:1000].contiguous(), qa[:1000].contiguous(), k_out))
+        secondary["single_pairing"] = {"latency_ms": ms_one, "batch_1000_ms": ms_k, "value": world * 1000 / (ms_k * 1e-3), "unit": "pairings/s",
+                                       "units_per_gpu": 1000, "ms": ms_k, "roofline_frac": 1000 / (ms_k * 1e-3) * MAC32_PER_PAIRING / peak_macs,
+                                       "config": "configs[0]: one pairing (latency-bound: one lane pair of one warp) and 1000 pairings as in bench_pairing_full"}
         from pairing_b200 import dist as pdist
         # configs[2]: multi_miller_loop product of 2^20 pairs per GPU + ONE shared final exponentiation
         nm = 1 << args.mm_log2
