@@ -116,6 +116,10 @@ int bls_g2_wnaf_table(bls_ctx*, const bls_g2* base, int window, bls_g2* table);
 /* CurveProjective::mul_assign (double-and-add), ec.rs:534-553 */
 int bls_g1_mul_batch(bls_ctx*, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n);
 int bls_g2_mul_batch(bls_ctx*, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n);
+/* CurveAffine::mul, ec.rs:174-177: $affine::mul_bits (MSB-first over all 256 bits, mixed additions) -- a different
+ * Jacobian representative of the same point as mul_assign on the projective form */
+int bls_g1_affine_mul_batch(bls_ctx*, const bls_g1_affine* a, const bls_fr_repr* k, bls_g1* out, size_t n);
+int bls_g2_affine_mul_batch(bls_ctx*, const bls_g2_affine* a, const bls_fr_repr* k, bls_g2* out, size_t n);
 /* CurveProjective::batch_normalization, ec.rs:246-294, in place */
 int bls_g1_batch_normalization(bls_ctx*, bls_g1* inout, size_t n);
 int bls_g2_batch_normalization(bls_ctx*, bls_g2* inout, size_t n);

@@ -285,9 +285,20 @@ using G2 = Curve<G2Point, G2AffinePoint, true>;
 
 struct G1Affine {
   static std::vector<G1PreparedPoint> prepare(const std::vector<G1AffinePoint>& p) { return p; }   // ec.rs:924-935
+  // CurveAffine::mul (ec.rs:174-177)
+  static std::vector<G1Point> mul(Gpu& g, const std::vector<G1AffinePoint>& p, const std::vector<FrRepr>& k) {
+    std::vector<G1Point> out(p.size());
+    g.check(bls_g1_affine_mul_batch(g.ctx(), p.data(), k.data(), out.data(), p.size()));
+    return out;
+  }
   static std::vector<Fq12> pairing_with(Gpu& g, const std::vector<G1AffinePoint>& p, const std::vector<G2AffinePoint>& q) { return Bls12::pairing(g, p, q); }
 };
 struct G2Affine {
+  static std::vector<G2Point> mul(Gpu& g, const std::vector<G2AffinePoint>& q, const std::vector<FrRepr>& k) {
+    std::vector<G2Point> out(q.size());
+    g.check(bls_g2_affine_mul_batch(g.ctx(), q.data(), k.data(), out.data(), q.size()));
+    return out;
+  }
   // G2Affine::prepare -> G2Prepared::from_affine (mod.rs:168-358)
   static std::vector<G2PreparedPoint> prepare(Gpu& g, const std::vector<G2AffinePoint>& q) {
     std::vector<G2PreparedPoint> out(q.size());

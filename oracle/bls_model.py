@@ -937,3 +937,14 @@ def scale_by_cofactor(p, g2):
         if (cof >> i) & 1:
             res = pt_add_mixed(F, res, p)
     return res
+
+
+def affine_mul(p, k, g2):
+    """CurveAffine::mul (ec.rs:174-177): mul_bits over all 256 bits of the FrRepr, MSB first, mixed additions."""
+    F = _F2 if g2 else _F1
+    res = pt_zero(F)
+    for i in range(255, -1, -1):
+        res = pt_double(F, res)
+        if (k >> i) & 1:
+            res = pt_add_mixed(F, res, p)
+    return res

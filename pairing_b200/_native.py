@@ -39,6 +39,7 @@ SYMBOLS = [
     "bls_g1_wnaf_fixed_base_batch", "bls_g2_wnaf_fixed_base_batch", "bls_g1_wnaf_table", "bls_g2_wnaf_table",
     "bls_fq12_pow_batch", "bls_fq12_pow_dev", "bls_fr_op_batch",
     "bls_miller_loop_shared_q_batch", "bls_pairing_shared_q_batch", "bls_miller_loop_shared_q_dev",
+    "bls_g1_affine_mul_batch", "bls_g2_affine_mul_batch",
     "bls_g1_point_from_x_batch", "bls_g2_point_from_x_batch", "bls_g1_scale_by_cofactor_batch", "bls_g2_scale_by_cofactor_batch",
     "bls_g1_decode_batch", "bls_g2_decode_batch", "bls_g1_encode_batch", "bls_g2_encode_batch",
     "bls_g1_wnaf_table_dev", "bls_g2_wnaf_table_dev", "bls_g1_wnaf_fixed_base_dev", "bls_g2_wnaf_fixed_base_dev",
@@ -117,6 +118,8 @@ def load():
         "bls_miller_loop_shared_q_batch": [vp, vp, vp, vp, sz],
         "bls_pairing_shared_q_batch": [vp, vp, vp, vp, sz],
         "bls_miller_loop_shared_q_dev": [vp, vp, vp, vp, sz, ci, vp],
+        "bls_g1_affine_mul_batch": [vp, vp, vp, vp, sz],
+        "bls_g2_affine_mul_batch": [vp, vp, vp, vp, sz],
         "bls_g1_point_from_x_batch": [vp, vp, vp, vp, vp, sz],
         "bls_g2_point_from_x_batch": [vp, vp, vp, vp, vp, sz],
         "bls_g1_scale_by_cofactor_batch": [vp, vp, vp, sz],
@@ -402,6 +405,16 @@ class Context:
         fn = self._lib.bls_g2_point_from_x_batch if g2 else self._lib.bls_g1_point_from_x_batch
         self._check(fn(self._ctx, _p(x), _p(gr), _p(out), _p(ok), x.shape[0]))
         return out, ok
+
+    def affine_mul(self, g2, affine, k):
+        """CurveAffine::mul for n (affine point, FrRepr) pairs -> Jacobian rows."""
+        affine, k = _arr(affine, W_G2A if g2 else W_G1A, "affine"), _arr(k, W_FR, "k")
+        if affine.shape[0] != k.shape[0]:
+            raise ValueError("affine and k must have the same length")
+        out = np.zeros((affine.shape[0], W_G2 if g2 else W_G1), dtype=np.uint64)
+        fn = self._lib.bls_g2_affine_mul_batch if g2 else self._lib.bls_g1_affine_mul_batch
+        self._check(fn(self._ctx, _p(affine), _p(k), _p(out), affine.shape[0]))
+        return out
 
     def scale_by_cofactor(self, g2, affine):
         affine = _arr(affine, W_G2A if g2 else W_G1A, "affine")

@@ -157,6 +157,7 @@ template <class F> __device__ __forceinline__ bool is_in_correct_subgroup(const 
 __device__ const uint32_t BLS_G1_COFACTOR[4] = {0x0000aaabu, 0x8c00aaabu, 0x5555e156u, 0x396c8c00u};
 __device__ const uint32_t BLS_G2_COFACTOR[16] = {0x1c7238e5u, 0xcf1c38e3u, 0x786f0c70u, 0x1616ec6eu, 0x3a6691aeu, 0x21537e29u, 0x4d9e82efu, 0xa628f1cbu,
                                                  0x2e5a7ddfu, 0xa68a205bu, 0x47085abau, 0xcd91de45u, 0x2876a202u, 0x091d5079u, 0x5414e7f1u, 0x05d543a9u};
+// (also CurveAffine::mul, ec.rs:174-177, with the 8 words of an FrRepr)
 template <class F> __device__ __forceinline__ void scale_by_cofactor(Jac<F>& res, const Aff<F>& p, const uint32_t* cof, int words) {
   pt_set_zero(res);
 #pragma unroll 1

@@ -467,6 +467,19 @@ __global__ void __launch_bounds__(128) k_scale_by_cofactor(const uint64_t* in, u
   st_jac(out + (size_t)PW * i, r);
 }
 
+// CurveAffine::mul (ec.rs:174-177): $affine::mul_bits over all 256 bits of the scalar, MSB first, mixed additions
+template <class F>
+__global__ void __launch_bounds__(128) k_affine_mul(const uint64_t* in, const uint64_t* k, uint64_t* out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int AW = 2 * FW<F>::W + 1, PW = 3 * FW<F>::W;
+  Aff<F> p; ld_aff(p, in + (size_t)AW * i);
+  const Scalar s = ld_scalar(k + 4 * i);
+  Jac<F> r;
+  scale_by_cofactor(r, p, s.v, 8);
+  st_jac(out + (size_t)PW * i, r);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Integer-multiply peak microbenchmarks (roofline denominator)
 // ------------------------------------------------------------------------------------------------
@@ -1003,6 +1016,25 @@ static int cofactor_host(bls_ctx* ctx, int degree, const void* in, void* out, si
 }
 int bls_g1_scale_by_cofactor_batch(bls_ctx* ctx, const bls_g1_affine* in, bls_g1* out, size_t n) { return cofactor_host(ctx, 1, in, out, n); }
 int bls_g2_scale_by_cofactor_batch(bls_ctx* ctx, const bls_g2_affine* in, bls_g2* out, size_t n) { return cofactor_host(ctx, 2, in, out, n); }
+
+static int affine_mul_host(bls_ctx* ctx, int degree, const void* a, const bls_fr_repr* k, void* out, size_t n) {
+  if (!ctx || (n && (!a || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  CK(cudaSetDevice(ctx->device));
+  const size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
+  const size_t ab = degree == 2 ? sizeof(bls_g2_affine) : sizeof(bls_g1_affine);
+  H2D(da, a, n * ab);
+  H2D(dk, k, n * sizeof(*k));
+  DALLOC(dout, n * pb);
+  if (degree == 2) k_affine_mul<Fp2><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)da.p, (const uint64_t*)dk.p, (uint64_t*)dout.p, n);
+  else k_affine_mul<Fp><<<blocks_for(n, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)da.p, (const uint64_t*)dk.p, (uint64_t*)dout.p, n);
+  LAUNCH_CHECK();
+  D2H(out, dout, n * pb);
+  SYNC();
+  return BLS_OK;
+}
+int bls_g1_affine_mul_batch(bls_ctx* ctx, const bls_g1_affine* a, const bls_fr_repr* k, bls_g1* out, size_t n) { return affine_mul_host(ctx, 1, a, k, out, n); }
+int bls_g2_affine_mul_batch(bls_ctx* ctx, const bls_g2_affine* a, const bls_fr_repr* k, bls_g2* out, size_t n) { return affine_mul_host(ctx, 2, a, k, out, n); }
 
 static int bn_host(bls_ctx* ctx, int degree, void* inout, size_t n) {
   if (!ctx || (n && !inout)) return BLS_ERR_INVALID_ARGUMENT;

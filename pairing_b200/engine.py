@@ -146,6 +146,10 @@ class G1Affine:
     def pairing_with(p, q, ctx=None):
         return Bls12.pairing(p, q, ctx)
 
+    # CurveAffine::mul (ec.rs:174-177): mul_bits with mixed additions -> Jacobian rows
+    @staticmethod
+    def mul(p, scalars, ctx=None): return _ctx(ctx).affine_mul(False, p, scalars)
+
     # CurveAffine::into_compressed / into_uncompressed (lib.rs:226-233 -> EncodedPoint::from_affine)
     @staticmethod
     def into_compressed(p, ctx=None): return _ctx(ctx).encode(False, p, True)
@@ -195,6 +199,9 @@ class G2Affine:
     @staticmethod
     def pairing_with(q, p, ctx=None):
         return Bls12.pairing(p, q, ctx)
+
+    @staticmethod
+    def mul(q, scalars, ctx=None): return _ctx(ctx).affine_mul(True, q, scalars)
 
     @staticmethod
     def into_compressed(q, ctx=None): return _ctx(ctx).encode(True, q, True)

@@ -36,6 +36,8 @@ extern "C" {
     pub fn bls_g2_decode_batch(ctx: *mut bls_ctx, bytes: *const u8, compressed: c_int, checked: c_int, out: *mut bls_g2_affine, status: *mut u8, n: usize) -> c_int;
     pub fn bls_g1_encode_batch(ctx: *mut bls_ctx, input: *const bls_g1_affine, compressed: c_int, bytes: *mut u8, n: usize) -> c_int;
     pub fn bls_g2_encode_batch(ctx: *mut bls_ctx, input: *const bls_g2_affine, compressed: c_int, bytes: *mut u8, n: usize) -> c_int;
+    pub fn bls_g1_affine_mul_batch(ctx: *mut bls_ctx, a: *const bls_g1_affine, k: *const bls_fr_repr, out: *mut bls_g1, n: usize) -> c_int;
+    pub fn bls_g2_affine_mul_batch(ctx: *mut bls_ctx, a: *const bls_g2_affine, k: *const bls_fr_repr, out: *mut bls_g2, n: usize) -> c_int;
     pub fn bls_g1_point_from_x_batch(ctx: *mut bls_ctx, x: *const bls_fq, greatest: *const u8, out: *mut bls_g1_affine, is_some: *mut u8, n: usize) -> c_int;
     pub fn bls_g2_point_from_x_batch(ctx: *mut bls_ctx, x: *const bls_fq2, greatest: *const u8, out: *mut bls_g2_affine, is_some: *mut u8, n: usize) -> c_int;
     pub fn bls_g1_scale_by_cofactor_batch(ctx: *mut bls_ctx, input: *const bls_g1_affine, out: *mut bls_g1, n: usize) -> c_int;

@@ -146,3 +146,27 @@ def test_point_from_x_and_scale_by_cofactor(ctx, g2):
     # ... while the unscaled points are (almost surely) not
     _, st0 = ctx.decode(g2, ctx.encode(g2, aff[good], True), True, checked=True)
     assert (st0 == m.DEC_NOT_IN_SUBGROUP).sum() >= len(good) - 1
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_affine_mul(ctx, g2):
+    """CurveAffine::mul (ec.rs:174-177): the Jacobian triple of mul_bits with mixed additions (big-int model on a few
+    elements), the same point as the projective wNAF / mul_assign after normalisation on all, infinity and scalar 0/1."""
+    import datagen as dg
+    n = 60
+    aff = (dg.g2_affine_points if g2 else dg.g1_affine_points)(n, 97, infinity_at=(4,))
+    k = dg.rand_scalars(n, 98)
+    got = ctx.affine_mul(g2, aff, k)
+    F = m._F2 if g2 else m._F1
+    for i in (0, 1, 2, 5, 20):                                 # scalars 0, 1, r-1, 2^129-ish, random
+        if g2:
+            x = (m.from_mont(m.from_limbs64(aff[i, 0:6])), m.from_mont(m.from_limbs64(aff[i, 6:12])))
+            y = (m.from_mont(m.from_limbs64(aff[i, 12:18])), m.from_mont(m.from_limbs64(aff[i, 18:24])))
+        else:
+            x, y = m.from_mont(m.from_limbs64(aff[i, 0:6])), m.from_mont(m.from_limbs64(aff[i, 6:12]))
+        want = m.affine_mul((x, y, bool(aff[i, -1])), m.from_limbs64(k[i]), g2)
+        assert got[i].tobytes() == m.to_bytes(want), i
+    proj = (o.g2_from_affine if g2 else o.g1_from_affine)(aff)
+    ref = (o.g2_op if g2 else o.g1_op)("mul", proj, k=k, threads=TH)
+    to_aff = o.g2_into_affine if g2 else o.g1_into_affine
+    assert np.array_equal(to_aff(got), to_aff(ref))
