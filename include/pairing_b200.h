@@ -165,7 +165,8 @@ enum {
   BLS_OP_FROB1 = 10, BLS_OP_FROB2 = 11, BLS_OP_FROB3 = 12, BLS_OP_CONJ = 13,
   BLS_OP_MUL_BY_014 = 14, /* Fq12 only: sparse operands b.c0.c0, b.c0.c1, b.c1.c1 (fq12.rs:34-48) */
   BLS_OP_MUL_BY_01 = 15,  /* Fq6 only: b.c0, b.c1 (fq6.rs:68-109) */
-  BLS_OP_MUL_BY_1 = 16    /* Fq6 only: b.c1 (fq6.rs:40-66) */
+  BLS_OP_MUL_BY_1 = 16,   /* Fq6 only: b.c1 (fq6.rs:40-66) */
+  BLS_OP_SQRT = 17        /* Fq, Fq2: SqrtField::sqrt (fq.rs:1147-1170, fq2.rs:167-221); ok = 0 for a non-residue */
 };
 int bls_field_op_batch(bls_ctx*, int degree, int op, const void* a, const void* b, void* out, uint8_t* ok, size_t n);
 

@@ -17,7 +17,7 @@ W_FQ, W_FQ2, W_FQ6, W_FQ12 = 6, 12, 36, 72
 W_G1A, W_G1, W_G2A, W_G2, W_FR, W_G2P = 13, 18, 25, 36, 4, 68 * 3 * 12 + 1
 
 OPS = dict(add=0, sub=1, mul=2, sqr=3, neg=4, dbl=5, inv=6, from_repr=7, into_repr=8, mul_nonres=9,
-           frob1=10, frob2=11, frob3=12, conj=13, mul_by_014=14, mul_by_01=15, mul_by_1=16)
+           frob1=10, frob2=11, frob3=12, conj=13, mul_by_014=14, mul_by_01=15, mul_by_1=16, sqrt=17)
 PT_OPS = dict(double=0, add=1, add_mixed=2, negate=3, sub=6)
 
 # every symbol include/pairing_b200.h declares (tests/test_abi.py checks the header against this list)

@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(128) k_fq_op(int op, const uint64_t* a, const 
       r = fp_mul(x, one);
       break;
     }
+    case BLS_OP_SQRT: good = f_sqrt(r, x); if (!good) r = fp_zero(); break;
   }
   st_fp(out + 6 * i, r);
   if (ok) ok[i] = good;
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(128) k_fq2_op(int op, const uint64_t* a, const
     case BLS_OP_INV: good = fp2_inv(r, x); if (!good) r = fp2_zero(); break;
     case BLS_OP_MUL_NONRES: r = fp2_mul_by_nonresidue(x); break;
     case BLS_OP_FROB1: r = fp2_frobenius(x, 1); break;
+    case BLS_OP_SQRT: good = f_sqrt(r, x); if (!good) r = fp2_zero(); break;
   }
   st_fp2(out + 12 * i, r);
   if (ok) ok[i] = good;
@@ -1103,6 +1105,7 @@ int bls_field_op_batch(bls_ctx* ctx, int degree, int op, const void* a, const vo
     case BLS_OP_NEG: valid = degree != 12; break;
     case BLS_OP_DBL: valid = degree <= 2; break;
     case BLS_OP_FROM_REPR: case BLS_OP_INTO_REPR: valid = degree == 1; break;
+    case BLS_OP_SQRT: valid = degree <= 2; break;
     case BLS_OP_MUL_NONRES: valid = degree == 2 || degree == 6; break;
     case BLS_OP_FROB1: valid = degree >= 2; break;
     case BLS_OP_FROB2: case BLS_OP_FROB3: valid = degree >= 6; break;

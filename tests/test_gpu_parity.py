@@ -324,3 +324,38 @@ def test_shared_q_miller_and_pairing(ctx):
         eq(ctx.pairing_shared_q(p, qp[j:j + 1]), o.pairing(p, rep_q, TH))
     eq(ctx.miller_loop_shared_q(p, ctx.g2_prepare(q[:1])), ctx.miller_loop(p, np.repeat(q[:1], n, 0)))
     assert ctx.pairing_shared_q(p[:0], qp[:1]).shape == (0, 72)
+
+
+def test_sqrt_fq_and_fq2(ctx):
+    """SqrtField::sqrt for Fq (fq.rs:1147-1170) and Fq2 (fq2.rs:167-221): the specific root of the reference's algorithm,
+    None for non-residues; includes the reference's two Fq2 known answers (fq2.rs:795-864)."""
+    n = 200
+    a = dg.rand_fq(n, 81)
+    a[0] = 0
+    sq = o.fq_op("sqr", a)[0]
+    both = np.concatenate([a, sq])
+    got, ok = ctx.field_op(1, "sqrt", both)
+    for i in range(len(both)):
+        v = m.from_mont(m.from_limbs64(both[i]))
+        want = m.fq_sqrt(v)
+        assert bool(ok[i]) == (want is not None)
+        if want is not None:
+            assert m.from_mont(m.from_limbs64(got[i])) == want
+    assert ok[n:].all() and 0 < ok[:n].sum() < n
+    a2 = dg.rand_field(n, 2, 82)
+    a2[0] = 0
+    sq2 = o.fq2_op("sqr", a2)[0]
+    L = m.from_limbs64
+    kat = [(L([0x476b4c309720e227, 0x34c2d04faffdab6, 0xa57e6fc1bab51fd9, 0xdb4a116b5bf74aa1, 0x1e58b2159dfe10e2, 0x7ca7da1f13606ac]),
+            L([0xfa8de88b7516d2c3, 0x371a75ed14f41629, 0x4cec2dca577a3eb6, 0x212611bca4e99121, 0x8ee5394d77afb3d, 0xec92336650e49d5])),
+           (L([0xb9f78429d1517a6b, 0x1eabfffeb153ffff, 0x6730d2a0f6b0f624, 0x64774b84f38512bf, 0x4b1ba7b6434bacd7, 0x1a0111ea397fe69a]), 0)]
+    krows = np.array([m.limbs64(m.to_mont(c0)) + m.limbs64(m.to_mont(c1)) for c0, c1 in kat], dtype=np.uint64)
+    both2 = np.concatenate([a2, sq2, krows])
+    got2, ok2 = ctx.field_op(2, "sqrt", both2)
+    for i in range(len(both2)):
+        v = (m.from_mont(m.from_limbs64(both2[i, :6])), m.from_mont(m.from_limbs64(both2[i, 6:])))
+        want = m.fq2_sqrt(v)
+        assert bool(ok2[i]) == (want is not None), i
+        if want is not None:
+            assert (m.from_mont(m.from_limbs64(got2[i, :6])), m.from_mont(m.from_limbs64(got2[i, 6:]))) == want, i
+    assert ok2[n:].all()

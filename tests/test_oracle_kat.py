@@ -365,3 +365,22 @@ def test_fr_constants_and_kats():
     assert m.fr_op_mont("into_repr", prod)[0] == rc
     assert m.fr_op_mont("from_repr", m.R_ORDER) == (0, False) and m.fr_op_mont("from_repr", m.R_ORDER + 1) == (0, False)
     assert m.fr_op_mont("inv", 0) == (0, False)
+
+
+def test_fq2_sqrt_kats():
+    """fq2.rs:795-864: the two Fq2 square-root known answers (the root the algorithm returns, not just a root)"""
+    L = m.from_limbs64
+    a = (L([0x476b4c309720e227, 0x34c2d04faffdab6, 0xa57e6fc1bab51fd9, 0xdb4a116b5bf74aa1, 0x1e58b2159dfe10e2, 0x7ca7da1f13606ac]),
+         L([0xfa8de88b7516d2c3, 0x371a75ed14f41629, 0x4cec2dca577a3eb6, 0x212611bca4e99121, 0x8ee5394d77afb3d, 0xec92336650e49d5]))
+    r = (L([0x40b299b2704258c5, 0x6ef7de92e8c68b63, 0x6d2ddbe552203e82, 0x8d7f1f723d02c1d3, 0x881b3e01b611c070, 0x10f6963bbad2ebc5]),
+         L([0xc099534fc209e752, 0x7670594665676447, 0x28a20faed211efe7, 0x6b852aeaf2afcb1b, 0xa4c93b08105d71a9, 0x8d7cfff94216330]))
+    assert m.fq2_sqrt(a) == r
+    b = (L([0xb9f78429d1517a6b, 0x1eabfffeb153ffff, 0x6730d2a0f6b0f624, 0x64774b84f38512bf, 0x4b1ba7b6434bacd7, 0x1a0111ea397fe69a]), 0)
+    rb = (0, L([0xb9fefffffd4357a3, 0x1eabfffeb153ffff, 0x6730d2a0f6b0f624, 0x64774b84f38512bf, 0x4b1ba7b6434bacd7, 0x1a0111ea397fe69a]))
+    assert m.fq2_sqrt(b) == rb
+    assert m.fq_sqrt(0) == 0 and m.fq2_sqrt((0, 0)) == (0, 0)
+    for v in (2, 3, 4, 5, 7, 12345678901234567890):          # fq.rs:2747-2775: sqrt(a^2) = +-a, sqrt(a)^2 = a
+        s = m.fq_sqrt(v * v % m.Q)
+        assert s in (v % m.Q, (-v) % m.Q)
+        t = m.fq_sqrt(v)
+        assert t is None or t * t % m.Q == v
