@@ -223,7 +223,7 @@ template <class F> struct SharedTable {
 
 // K points per thread (pt_wnaf_run_lazy): thread t owns points t, t + T, ..., t + (K-1) T
 #ifndef BLS_WNAF_K
-#define BLS_WNAF_K 2
+#define BLS_WNAF_K 3      /* G1: 9.57 M muls/s at 2^22 against 9.33 M for K = 2 (lane efficiency 95 % vs 91 %) */
 #endif
 #ifndef BLS_WNAF_K_G2
 #define BLS_WNAF_K_G2 2
