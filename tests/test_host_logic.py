@@ -131,3 +131,20 @@ def test_rust_shim_binds_every_host_entry_point():
     skip = ("_dev", "_scratch_bytes", "bls_imad_peak", "bls_ctx_device", "bls_ctx_sm_count", "bls_ctx_launch_count", "bls_field_op_batch")
     missing = [n for n in names if not n.endswith(skip[:2]) and n not in skip and ("fn %s(" % n) not in ffi]
     assert not missing, missing
+
+
+def test_bench_reference_arm_runs_on_cpu_and_prints_the_contract_line():
+    """`bench.py --impl reference` (the C restatement on the host cores) needs no GPU and prints one JSON line with the
+    contract's keys; under torchrun only rank 0 prints."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.check_output([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                                  text=True, timeout=300)
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "pairings/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "pairings/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    out = subprocess.check_output([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                                  text=True, timeout=60, env=env)
+    assert out.strip() == ""
