@@ -175,40 +175,6 @@ template <class D> __device__ __forceinline__ int wnaf_form(D* digits, Scalar c,
   return n;
 }
 
-// Wnaf::new().scalar(k).base(g)  (wnaf.rs:111-128, 158-164) with an explicit window
-template <class F> __device__ __forceinline__ void pt_wnaf_mul(Jac<F>& out, const Jac<F>& base, const Scalar& k, int window,
-                                                          Jac<F>* table, int8_t* digits) {
-  // wnaf_table, wnaf.rs:4-15: table[i] = (2i+1) * base by repeated projective additions of 2*base
-  {
-    Jac<F> b = base, dbl = base;
-    pt_double(dbl);
-    const int tsize = 1 << (window - 1);
-#pragma unroll 1
-    for (int i = 0; i < tsize; i++) { table[i] = b; pt_add(b, dbl); }
-  }
-  int nd = wnaf_form(digits, k, window);
-  // wnaf_exp, wnaf.rs:49-71
-  Jac<F> result;
-  pt_set_zero(result);
-  bool found_one = false;
-#pragma unroll 1
-  for (int i = nd - 1; i >= 0; i--) {
-    int n = digits[i];
-    if (found_one) pt_double(result);
-    if (n != 0) {
-      found_one = true;
-      if (n > 0) {
-        pt_add(result, table[n >> 1]);
-      } else {
-        Jac<F> t = table[(-n) >> 1];     // sub_assign: copy, negate, add (lib.rs:156-160)
-        pt_negate(t);
-        pt_add(result, t);
-      }
-    }
-  }
-  out = result;
-}
-
 // wnaf_exp with the warp's lanes DECOUPLED: every lane walks its own (double, add) sequence -- for digit i
 // from the top: a double once a non-zero digit has been seen, then an add/sub if digit i is non-zero -- but
 // the warp only ever executes one of the two group operations at a time.  Executing both at every digit

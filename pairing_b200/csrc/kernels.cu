@@ -190,30 +190,11 @@ __global__ void __launch_bounds__(128) k_fq12_product(const uint64_t* in, size_t
 // ------------------------------------------------------------------------------------------------
 // Curve kernels
 // ------------------------------------------------------------------------------------------------
-template <class F, bool IS_G2, int MAXT>
-__global__ void __launch_bounds__(128) k_wnaf_mul(const uint64_t* bases, const uint64_t* k, uint64_t* out, size_t n, int window) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const int PW = 3 * FW<F>::W;
-  Jac<F> base, res;
-  ld_jac(base, bases + (size_t)PW * i);
-  Scalar s = ld_scalar(k + 4 * i);
-  int w = window;
-  if (w == 0) {
-    int nb = scalar_num_bits(s);
-    w = IS_G2 ? g2_window_for_bits(nb) : g1_window_for_bits(nb);
-  }
-  Jac<F> table[MAXT];   // 2^(w-1) entries: 8 covers the per-scalar heuristics (w <= 4)
-  int8_t digits[260];
-  pt_wnaf_mul(res, base, s, w, table, digits);
-  st_jac(out + (size_t)PW * i, res);
-}
-
 #ifndef BLS_WNAF_MINB
 #define BLS_WNAF_MINB 3
 #endif
-template <class F, int K> struct LocalTables {
-  Jac<F> t[K][8];
+template <class F, int K, int MAXT> struct LocalTables {
+  Jac<F> t[K][MAXT];
   __device__ __forceinline__ Jac<F> get(int j, int e) const { return t[j][e]; }
 };
 template <class F> struct SharedTable {
@@ -229,13 +210,15 @@ template <class F> struct SharedTable {
 #define BLS_WNAF_K_G2 2
 #endif
 // blocks per SM: 4 for G1 (128 registers), 3 for G2 (168) -- measured at 2^20 points: 9.17 vs 9.01 M G1 muls/s, 3.30 vs 2.90 M G2 muls/s
-template <class F, bool IS_G2, int K>
+// MAXT = table entries per point: 8 for the windows the per-scalar heuristics pick (2..4, ec.rs:895-905, 1586-1596),
+// 64 (K = 1) for the explicit windows 5..7 of wnaf_table / wnaf_exp
+template <class F, bool IS_G2, int K, int MAXT>
 __global__ void __launch_bounds__(128, IS_G2 ? BLS_WNAF_MINB : BLS_WNAF_MINB + 1) k_wnaf_mul_lazyk(const uint64_t* bases, const uint64_t* k, uint64_t* out, size_t n, int window) {
   const size_t T = (size_t)gridDim.x * blockDim.x;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int PW = 3 * FW<F>::W;
   Jac<F> res[K];
-  LocalTables<F, K> table;
+  LocalTables<F, K, MAXT> table;
   int8_t digits[K][260];
   WnafState<K> st;
 #pragma unroll 1
@@ -259,7 +242,7 @@ __global__ void __launch_bounds__(128, IS_G2 ? BLS_WNAF_MINB : BLS_WNAF_MINB + 1
     Jac<F> b = base, dbl = base;
     pt_double(dbl);
 #pragma unroll 1
-    for (int e = 0; e < 8; e++) {          // wnaf_table, wnaf.rs:4-15 (the last add is unused)
+    for (int e = 0; e < MAXT; e++) {       // wnaf_table, wnaf.rs:4-15 (the last add is unused)
       if (e < tsize) { table.t[j][e] = b; if (e + 1 < tsize) pt_add(b, dbl); }
     }
     st.i[j] = wnaf_form(digits[j], s, w) - 1;
@@ -656,8 +639,8 @@ int bls_g1_wnaf_mul_dev(bls_ctx* ctx, const bls_g1* bases, const bls_fr_repr* k,
   if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   CK(cudaSetDevice(ctx->device));
-  if (window <= 4) k_wnaf_mul_lazyk<Fp, false, BLS_WNAF_K><<<blocks_for((n + BLS_WNAF_K - 1) / BLS_WNAF_K, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
-  else k_wnaf_mul<Fp, false, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  if (window <= 4) k_wnaf_mul_lazyk<Fp, false, BLS_WNAF_K, 8><<<blocks_for((n + BLS_WNAF_K - 1) / BLS_WNAF_K, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  else k_wnaf_mul_lazyk<Fp, false, 1, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   LAUNCH_CHECK();
   return BLS_OK;
 }
@@ -665,8 +648,8 @@ int bls_g2_wnaf_mul_dev(bls_ctx* ctx, const bls_g2* bases, const bls_fr_repr* k,
   if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   CK(cudaSetDevice(ctx->device));
-  if (window <= 4) k_wnaf_mul_lazyk<Fp2, true, BLS_WNAF_K_G2><<<blocks_for((n + BLS_WNAF_K_G2 - 1) / BLS_WNAF_K_G2, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
-  else k_wnaf_mul<Fp2, true, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  if (window <= 4) k_wnaf_mul_lazyk<Fp2, true, BLS_WNAF_K_G2, 8><<<blocks_for((n + BLS_WNAF_K_G2 - 1) / BLS_WNAF_K_G2, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  else k_wnaf_mul_lazyk<Fp2, true, 1, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   LAUNCH_CHECK();
   return BLS_OK;
 }

@@ -183,13 +183,23 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller_sha
 }
 
 // ONE miller_loop over n prepared pairs: lane pair t owns pairs t, t+T, ... and one accumulator (see k_pair_multi_miller)
+__device__ __forceinline__ PLine mm_prepared_line(const uint64_t* p, const uint64_t* qp, size_t n, size_t i, int idx) {
+  const bool in_range = i < n;
+  if (!in_range) i = n - 1;
+  const uint64_t* pi = p + G1A_W * i;
+  const uint64_t* qi = qp + (size_t)G2P_W * i;
+  const bool dead = !in_range || pi[12] != 0 || qi[G2P_W - 1] != 0;
+  PCoeffs c;
+  ld_pcoeffs(c, qi + 36 * idx);
+  pcoeffs_set_one_if(dead, c);
+  return p_line(c, ld_fp(pi), ld_fp(pi + 6));
+}
 __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_multi_miller_prepared(const uint64_t* p, const uint64_t* qp, size_t n, uint64_t* partials) {
   const size_t T = ((size_t)gridDim.x * blockDim.x) >> 1;
   const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
   const size_t per = (n + T - 1) / T;
   P12 f;
   p12_one(f);
-  PCoeffs c;
   int idx = 0;
 #pragma unroll 1
   for (int b = BLS_LOOP_TOP; b >= -1; b--) {
@@ -197,16 +207,10 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_multi_mill
 #pragma unroll 1
     for (int rep = 0; rep < (bit ? 2 : 1); rep++) {
 #pragma unroll 1
-      for (size_t j = 0; j < per; j++) {
-        size_t i = t + j * T;
-        const bool in_range = i < n;
-        if (!in_range) i = n - 1;
-        const uint64_t* pi = p + G1A_W * i;
-        const uint64_t* qi = qp + (size_t)G2P_W * i;
-        const bool dead = !in_range || pi[12] != 0 || qi[G2P_W - 1] != 0;
-        ld_pcoeffs(c, qi + 36 * idx);
-        pcoeffs_set_one_if(dead, c);
-        p_ell(f, c, ld_fp(pi), ld_fp(pi + 6));
+      for (size_t j = 0; j < per; j += 2) {          // two pairs at a time: see p12_mul_by_line_pair
+        const PLine l = mm_prepared_line(p, qp, n, t + j * T, idx);
+        if (j + 1 < per) p12_mul_by_line_pair(f, l, mm_prepared_line(p, qp, n, t + (j + 1) * T, idx));
+        else p12_mul_by_014(f, l.c0, l.c1, l.c4);
       }
       idx++;
     }
@@ -274,46 +278,44 @@ __device__ __forceinline__ void st_pjac_soa(uint32_t* s, size_t n, size_t pair, 
 #pragma unroll
   for (int k = 0; k < 36; k++) b[(size_t)k * n] = w[k];
 }
+// one step (phase 0: doubling, phase 1: addition) of pair i's running point, and its line value at P_i
+__device__ __forceinline__ PLine mm_step_line(const uint64_t* p, const uint64_t* q, size_t n, uint32_t* rstate, size_t i, int phase, int b) {
+  const bool in_range = i < n;
+  if (!in_range) i = n - 1;
+  const uint64_t* pi = p + G1A_W * i;
+  const uint64_t* qi = q + G2A_W * i;
+  const bool dead = !in_range || pi[12] != 0 || qi[24] != 0;
+  PJac r;
+  PCoeffs c;
+  if (phase == 0) {
+    if (b == BLS_LOOP_TOP) { r.x = ld_p2(qi); r.y = ld_p2(qi + 12); r.z = p2_one(); }
+    else ld_pjac_soa(r, rstate, n, i);
+    pg2_doubling_step(r, c);
+    if (b >= 0 && in_range) st_pjac_soa(rstate, n, i, r);
+  } else {
+    ld_pjac_soa(r, rstate, n, i);
+    pg2_addition_step(r, ld_p2(qi), ld_p2(qi + 12), c);
+    if (in_range) st_pjac_soa(rstate, n, i, r);
+  }
+  pcoeffs_set_one_if(dead, c);
+  return p_line(c, ld_fp(pi), ld_fp(pi + 6));
+}
 __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_multi_miller(const uint64_t* p, const uint64_t* q, size_t n, uint32_t* rstate, uint64_t* partials) {
   const size_t T = ((size_t)gridDim.x * blockDim.x) >> 1;                       // lane pairs
   const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
   const size_t per = (n + T - 1) / T;                                            // loop trips, uniform over the grid
   P12 f;
   p12_one(f);
-  PCoeffs c;
-  PJac r;
 #pragma unroll 1
   for (int b = BLS_LOOP_TOP; b >= -1; b--) {   // b == -1 is the trailing doubling step (mod.rs:92-94)
     const bool bit = b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull);
 #pragma unroll 1
-    for (size_t j = 0; j < per; j++) {
-      size_t i = t + j * T;
-      const bool in_range = i < n;
-      if (!in_range) i = n - 1;
-      const uint64_t* pi = p + G1A_W * i;
-      const uint64_t* qi = q + G2A_W * i;
-      const bool dead = !in_range || pi[12] != 0 || qi[24] != 0;
-      if (b == BLS_LOOP_TOP) { r.x = ld_p2(qi); r.y = ld_p2(qi + 12); r.z = p2_one(); }
-      else ld_pjac_soa(r, rstate, n, i);
-      pg2_doubling_step(r, c);
-      pcoeffs_set_one_if(dead, c);
-      p_ell(f, c, ld_fp(pi), ld_fp(pi + 6));
-      if (b >= 0 && in_range) st_pjac_soa(rstate, n, i, r);
-    }
-    if (bit) {
+    for (int phase = 0; phase < (bit ? 2 : 1); phase++) {
 #pragma unroll 1
-      for (size_t j = 0; j < per; j++) {
-        size_t i = t + j * T;
-        const bool in_range = i < n;
-        if (!in_range) i = n - 1;
-        const uint64_t* pi = p + G1A_W * i;
-        const uint64_t* qi = q + G2A_W * i;
-        const bool dead = !in_range || pi[12] != 0 || qi[24] != 0;
-        ld_pjac_soa(r, rstate, n, i);
-        pg2_addition_step(r, ld_p2(qi), ld_p2(qi + 12), c);
-        pcoeffs_set_one_if(dead, c);
-        p_ell(f, c, ld_fp(pi), ld_fp(pi + 6));
-        if (in_range) st_pjac_soa(rstate, n, i, r);
+      for (size_t j = 0; j < per; j += 2) {          // two pairs at a time: see p12_mul_by_line_pair
+        const PLine l = mm_step_line(p, q, n, rstate, t + j * T, phase, b);
+        if (j + 1 < per) p12_mul_by_line_pair(f, l, mm_step_line(p, q, n, rstate, t + (j + 1) * T, phase, b));
+        else p12_mul_by_014(f, l.c0, l.c1, l.c4);
       }
     }
     if (b >= 0) p12_sqr(f, f);

@@ -84,6 +84,25 @@ def test_pairing_full_batch(eng, data):
     assert np.array_equal(eng.ctx.multi_miller_loop(_np(pa)[sub], _np(qa)[sub]), _np(eng.fq12_product(ml[sub].contiguous())))
 
 
+def test_multi_miller_ragged_trip_counts(eng, data):
+    """The multi-pairing kernels multiply the lines of two pairs before touching the accumulator; with T lane pairs a
+    lane pair runs ceil(n / T) trips, so n picks the shape: an odd trip count (a single line left over), a last trip
+    that only some lane pairs fill, infinity members on both slots.  == product of the single Miller values, for the
+    steps-on-the-fly kernel (device buffers) and the G2Prepared kernel (host buffers)."""
+    T = eng.ctx.sm_count * 2 * 64                     # lane pairs of a full grid (kernels_pair.cu: mm_threads)
+    for n in (T + 1, 2 * T - 3, 2 * T + 64, 3 * T - 1000):
+        pa, qa = data[0][:n].clone(), data[1][:n].clone()
+        pa[3, 12] = 1; qa[T + 3 if n > T + 3 else 0, 24] = 1; pa[n - 1, 12] = 1
+        ml = eng.miller_loop_batch(pa, qa)
+        assert torch.equal(eng.multi_miller_loop(pa, qa), eng.fq12_product(ml)), n
+    n = T + 70                                        # prepared coefficients: 19 592 B per pair, keep it small
+    pa, qa = data[0][:n].clone(), data[1][:n].clone()
+    pa[1, 12] = 1; qa[T + 1, 24] = 1
+    want = _np(eng.fq12_product(eng.miller_loop_batch(pa, qa)))
+    prep = eng.g2_prepare(qa)
+    assert np.array_equal(eng.ctx.multi_miller_loop_prepared(_np(pa), _np(prep)), want)
+
+
 def test_bilinearity_full_batch(eng, data):
     """e([a]P, Q) == e(P, [a]Q) for 2^16 independent (P, Q, a): wNAF (G1 and G2), batch normalisation, pairing."""
     pa, qa, g1_jac, ks = data
