@@ -66,6 +66,7 @@ if "mm" not in skip:
     res = []
     ms = timeit(lambda: res.append(eng.multi_miller_loop(pa[:nm], qa[:nm])))
     report("multi_miller_loop (config 3)", nm, ms, 4684 * 300)
+    print("  multi-Miller value checksum %016x" % int(res[-1].cpu().numpy().view(np.uint64).sum(dtype=np.uint64)))
     want = o.multi_miller_loop(pa[:C].cpu().numpy().view(np.uint64), qa[:C].cpu().numpy().view(np.uint64)) if hasattr(o, "multi_miller_loop") else None
     if want is not None:
         got = eng.multi_miller_loop(pa[:C].contiguous(), qa[:C].contiguous()).cpu().numpy().view(np.uint64)
