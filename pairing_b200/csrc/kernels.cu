@@ -209,11 +209,14 @@ template <class F> struct SharedTable {
 #ifndef BLS_WNAF_K_G2
 #define BLS_WNAF_K_G2 2
 #endif
-// blocks per SM: 4 for G1 (128 registers), 3 for G2 (168) -- measured at 2^20 points: 9.17 vs 9.01 M G1 muls/s, 3.30 vs 2.90 M G2 muls/s
+// blocks per SM: 3 for G2 (168 registers; 3.29 M muls/s at 2^20 against 3.19 M with 2 and 2.90 M with 4), BLS_WNAF_MINB_G1 for G1
+#ifndef BLS_WNAF_MINB_G1
+#define BLS_WNAF_MINB_G1 5   /* 96 registers: 9.69 M G1 muls/s at 2^22 against 9.57 M with 4 blocks and 9.40 M with 6 (one run) */
+#endif
 // MAXT = table entries per point: 8 for the windows the per-scalar heuristics pick (2..4, ec.rs:895-905, 1586-1596),
 // 64 (K = 1) for the explicit windows 5..7 of wnaf_table / wnaf_exp
 template <class F, bool IS_G2, int K, int MAXT>
-__global__ void __launch_bounds__(128, IS_G2 ? BLS_WNAF_MINB : BLS_WNAF_MINB + 1) k_wnaf_mul_lazyk(const uint64_t* bases, const uint64_t* k, uint64_t* out, size_t n, int window) {
+__global__ void __launch_bounds__(128, IS_G2 ? BLS_WNAF_MINB : BLS_WNAF_MINB_G1) k_wnaf_mul_lazyk(const uint64_t* bases, const uint64_t* k, uint64_t* out, size_t n, int window) {
   const size_t T = (size_t)gridDim.x * blockDim.x;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int PW = 3 * FW<F>::W;
