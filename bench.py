@@ -336,8 +336,10 @@ def run_ours(args):
         def mm_run():
             mm = pdist.multi_miller_loop_sharded(eng.multi_miller_loop, eng.fq12_product, pm, qm)
             return eng.final_exponentiation(mm)[0]
-        ms, fe = timed(mm_run)
-        secondary["multi_miller_loop"] = entry(nm, ms, MAC32_PER_MM_PAIR, unit="pairs/s",
+        mm_run()                                                    # one untimed full-size pass, then the mean of three
+        ms3, fe = timed(lambda: [mm_run() for _ in range(3)][-1])
+        ms = ms3 / 3
+        secondary["multi_miller_loop"] = entry(nm, ms, MAC32_PER_MM_PAIR, unit="pairs/s", passes=3,
                                                collective="all_gather of one 576-byte Fq12 per rank (NCCL)" if world > 1 else "none (1 rank)",
                                                config="configs[2]: product of 2^%d pairs per GPU, one final exponentiation" % args.mm_log2)
         del pm, qm
