@@ -275,17 +275,25 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_fq12_pow(c
 // touches one contiguous 4608-byte block.  (A word-major array over all n -- plane stride n words -- measured bimodal,
 // 222 or 252 ms per 2^20 pairs from one process to the next.)
 __host__ __device__ __forceinline__ size_t mm_rstate_words(size_t n) { return ((n + 15) / 16) * (36 * 32); }
+// BLS_MM_STREAM = 1 marks these accesses evict-first (ld.global.cs / st.global.cs): the 302 MB of running points of a 2^20
+// batch stream through L2 once per loop iteration and compete with the 62 MB of local memory the kernel keeps there.
+// Unmeasured (default off): an A/B candidate for the two timing modes described in DESIGN.md section 4.
+#ifndef BLS_MM_STREAM
+#define BLS_MM_STREAM 0
+#endif
 __device__ __forceinline__ void ld_pjac_blk(PJac& r, const uint32_t* s, size_t pair) {
   uint32_t* w = reinterpret_cast<uint32_t*>(&r);
   const uint32_t* b = s + (pair >> 4) * (36 * 32) + 2 * (pair & 15) + pair_c();
 #pragma unroll
-  for (int k = 0; k < 36; k++) w[k] = b[k * 32];
+  for (int k = 0; k < 36; k++) w[k] = BLS_MM_STREAM ? __ldcs(b + k * 32) : b[k * 32];
 }
 __device__ __forceinline__ void st_pjac_blk(uint32_t* s, size_t pair, const PJac& r) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
   uint32_t* b = s + (pair >> 4) * (36 * 32) + 2 * (pair & 15) + pair_c();
 #pragma unroll
-  for (int k = 0; k < 36; k++) b[k * 32] = w[k];
+  for (int k = 0; k < 36; k++) {
+    if (BLS_MM_STREAM) __stcs(b + k * 32, w[k]); else b[k * 32] = w[k];
+  }
 }
 // one step (phase 0: doubling, phase 1: addition) of pair i's running point, and its line value at P_i
 __device__ __forceinline__ PLine mm_step_line(const uint64_t* p, const uint64_t* q, size_t n, uint32_t* rstate, size_t i, int phase, int b) {

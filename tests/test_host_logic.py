@@ -148,3 +148,35 @@ def test_bench_reference_arm_runs_on_cpu_and_prints_the_contract_line():
     out = subprocess.check_output([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
                                   text=True, timeout=60, env=env)
     assert out.strip() == ""
+
+
+def test_line_pair_product_is_two_mul_by_014():
+    """The multi-pairing kernels multiply the line values of two pairs with each other first (pair_tower.cuh:
+    p12_mul_by_line_pair -- 6 Fq2 products for sparse x sparse, 17 for f x the 5-coefficient result).  The big-int model
+    of exactly those formulas equals two mul_by_014 (fq12.rs:34-48) on random and degenerate operands, i.e. the kernel
+    changes the order of the multiplications, not the value of f."""
+    import random
+    import bls_model as m
+    rnd = random.Random(0xE11)
+    r2 = lambda: (rnd.randrange(m.Q), rnd.randrange(m.Q))
+    r6 = lambda: (r2(), r2(), r2())
+    add, sub, mul = m.fq2_add, m.fq2_sub, m.fq2_mul
+
+    def line_pair(f, l, k):
+        m00, m11, m44 = mul(l[0], k[0]), mul(l[1], k[1]), mul(l[2], k[2])
+        c01 = sub(sub(mul(add(l[0], l[1]), add(k[0], k[1])), m00), m11)
+        d1 = sub(sub(mul(add(l[0], l[2]), add(k[0], k[2])), m00), m44)
+        d2 = sub(sub(mul(add(l[1], l[2]), add(k[1], k[2])), m11), m44)
+        lm0 = (add(m00, m.fq2_mul_by_nonresidue(m44)), c01, m11)
+        aa = m.fq6_mul(f[0], lm0)
+        bb = m.fq6_mul_by_nonresidue(m.fq6_mul_by_01(f[1], d1, d2))
+        s = m.fq6_mul(m.fq6_add(f[1], f[0]), (lm0[0], add(lm0[1], d1), add(lm0[2], d2)))
+        return (m.fq6_add(m.fq6_mul_by_nonresidue(bb), aa), m.fq6_sub(m.fq6_sub(s, aa), bb))
+
+    one, zero = (1, 0), (0, 0)
+    cases = [((r6(), r6()), (r2(), r2(), r2()), (r2(), r2(), r2())) for _ in range(12)]
+    cases.append(((r6(), r6()), (r2(), r2(), r2()), (one, zero, zero)))          # a skipped pair: the line is one
+    cases.append(((r6(), r6()), (one, zero, zero), (one, zero, zero)))
+    cases.append((((one, zero, zero), (zero, zero, zero)), (r2(), r2(), r2()), (r2(), zero, r2())))
+    for f, l, k in cases:
+        assert line_pair(f, l, k) == m.fq12_mul_by_014(m.fq12_mul_by_014(f, *l), *k)
