@@ -210,7 +210,8 @@ int bls_g2_batch_normalization_dev(bls_ctx*, bls_g2* inout, size_t n, void* scra
  * (MEASURED_PEAKS.json has no integer figure).  variant 0 = chains of dependent IMAD.WIDE.U32
  * (32x32->64, the only multiply in the loop -- checked on the SASS by tests/test_abi.py),
  * 1 = back-to-back fp_mul (300 MAC32 each), 2 = 32-bit IMAD, 3 = carry-linked
- * IMAD.WIDE.U32.X rows only (mad.lo.cc / madc.hi.cc chains, no reduction).
+ * IMAD.WIDE.U32.X rows only (mad.lo.cc / madc.hi.cc chains, no reduction), 4 = back-to-back dedicated squarings
+ * (fq.rs:963-1016; 234 MAC32 each).
  * Returns multiply-accumulates per second in *macs_per_s and the kernel time in *ms. */
 int bls_imad_peak(bls_ctx*, int variant, int iters, double* macs_per_s, double* ms);
 

@@ -157,12 +157,18 @@ struct Bls12 {
   }
 };
 
+// every binary wrapper takes one n from the first vector: a shorter second vector would be read past its end by the H2D copy
+inline void require_same_length(size_t a, size_t b, const char* what) {
+  if (a != b) throw Error(BLS_ERR_INVALID_ARGUMENT, std::string(what) + ": length mismatch");
+}
+
 // ------------------------------------------------------------------------------------------------ scalar field
 // PrimeField / Field for Fr (fr.rs:271-572), batch-shaped.  Values are Montgomery-form `bls_fr`; `from_repr` returns the
 // per-element validity the reference reports as Err(NotInField).
 struct FrField {
   using Elem = bls_fr;
   static std::vector<Elem> op(Gpu& g, int o, const std::vector<Elem>& a, const std::vector<Elem>* b, std::vector<uint8_t>* ok = nullptr) {
+    if (b) require_same_length(a.size(), b->size(), "FrField::op");
     std::vector<Elem> out(a.size());
     std::vector<uint8_t> good(a.size());
     g.check(bls_fr_op_batch(g.ctx(), o, a.data(), b ? b->data() : nullptr, out.data(), good.data(), a.size()));
@@ -207,22 +213,26 @@ template <class Proj, class Aff, bool IS_G2> struct Curve {
   static std::vector<Proj> double_(Gpu& g, const std::vector<Proj>& a) { return unary(g, BLS_PT_DOUBLE, a); }
   static std::vector<Proj> negate(Gpu& g, const std::vector<Proj>& a) { return unary(g, BLS_PT_NEGATE, a); }
   static std::vector<Proj> add_assign(Gpu& g, const std::vector<Proj>& a, const std::vector<Proj>& b) {
+    require_same_length(a.size(), b.size(), "add_assign");
     std::vector<Proj> out(a.size());
     g.check(op(g, BLS_PT_ADD, a.data(), b.data(), out.data(), a.size()));
     return out;
   }
   static std::vector<Proj> sub_assign(Gpu& g, const std::vector<Proj>& a, const std::vector<Proj>& b) {
+    require_same_length(a.size(), b.size(), "sub_assign");
     std::vector<Proj> out(a.size());
     g.check(op(g, BLS_PT_SUB, a.data(), b.data(), out.data(), a.size()));
     return out;
   }
   static std::vector<Proj> add_assign_mixed(Gpu& g, const std::vector<Proj>& a, const std::vector<Aff>& b) {
+    require_same_length(a.size(), b.size(), "add_assign_mixed");
     std::vector<Proj> out(a.size());
     g.check(op(g, BLS_PT_ADD_MIXED, a.data(), b.data(), out.data(), a.size()));
     return out;
   }
   // CurveProjective::mul_assign: double-and-add (ec.rs:534-553)
   static std::vector<Proj> mul_assign(Gpu& g, const std::vector<Proj>& a, const std::vector<FrRepr>& k) {
+    require_same_length(a.size(), k.size(), "mul_assign");
     std::vector<Proj> out(a.size());
     if constexpr (IS_G2) g.check(bls_g2_mul_batch(g.ctx(), a.data(), k.data(), out.data(), a.size()));
     else g.check(bls_g1_mul_batch(g.ctx(), a.data(), k.data(), out.data(), a.size()));
@@ -287,6 +297,7 @@ struct G1Affine {
   static std::vector<G1PreparedPoint> prepare(const std::vector<G1AffinePoint>& p) { return p; }   // ec.rs:924-935
   // CurveAffine::mul (ec.rs:174-177)
   static std::vector<G1Point> mul(Gpu& g, const std::vector<G1AffinePoint>& p, const std::vector<FrRepr>& k) {
+    require_same_length(p.size(), k.size(), "G1Affine::mul");
     std::vector<G1Point> out(p.size());
     g.check(bls_g1_affine_mul_batch(g.ctx(), p.data(), k.data(), out.data(), p.size()));
     return out;
@@ -295,6 +306,7 @@ struct G1Affine {
 };
 struct G2Affine {
   static std::vector<G2Point> mul(Gpu& g, const std::vector<G2AffinePoint>& q, const std::vector<FrRepr>& k) {
+    require_same_length(q.size(), k.size(), "G2Affine::mul");
     std::vector<G2Point> out(q.size());
     g.check(bls_g2_affine_mul_batch(g.ctx(), q.data(), k.data(), out.data(), q.size()));
     return out;

@@ -399,7 +399,9 @@ class Context:
     def point_from_x(self, g2, x, greatest):
         """$affine::get_point_from_x for n x-coordinates (Montgomery limbs) -> (affine rows, is_some)."""
         x = _arr(x, W_FQ2 if g2 else W_FQ, "x")
-        gr = np.ascontiguousarray(greatest, dtype=np.uint8)
+        gr = np.ascontiguousarray(greatest, dtype=np.uint8).reshape(-1)
+        if gr.shape[0] != x.shape[0]:
+            raise ValueError("x and greatest must have the same length")
         out = np.zeros((x.shape[0], W_G2A if g2 else W_G1A), dtype=np.uint64)
         ok = np.zeros(x.shape[0], dtype=np.uint8)
         fn = self._lib.bls_g2_point_from_x_batch if g2 else self._lib.bls_g1_point_from_x_batch

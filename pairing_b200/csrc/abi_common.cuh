@@ -74,6 +74,25 @@ struct bls_ctx {
     }                                                                                 \
   } while (0)
 
+// Every entry point runs on ctx->device and leaves the caller's current device as it found it (a host that shares the
+// process with torch or with another context must not have its current device switched under it).
+struct DevGuard {
+  int prev = -1;
+  bool switched = false;
+  cudaError_t enter(int dev) {
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return e;
+    if (prev == dev) return cudaSuccess;
+    e = cudaSetDevice(dev);
+    switched = e == cudaSuccess;
+    return e;
+  }
+  ~DevGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define USE_DEVICE(ctx) \
+  DevGuard dev_guard_;  \
+  CK(dev_guard_.enter((ctx)->device))
+
 static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 static const int TPB = 128;
 

@@ -528,6 +528,19 @@ __global__ void __launch_bounds__(256) k_fpmul_peak(uint32_t seed, int iters, ui
   if (x.v[0] == 0x1234567u && y.v[3] == 7u) sink[0] = x.v[1];
 }
 
+// the dedicated squaring (fp_sqr_gen.cuh): 222 wide MACs + 12 IMAD = 234 MAC32 per squaring, two independent chains
+__global__ void __launch_bounds__(256) k_fpsqr_peak(uint32_t seed, int iters, uint64_t* sink) {
+  Fp x = fp_one(), y = fp_r2();
+  x.v[0] ^= seed ^ threadIdx.x;
+  y.v[1] ^= seed + 77u * threadIdx.x;
+#pragma unroll 1
+  for (int it = 0; it < iters; it++) {
+    x = fp_sqr_inline(x);
+    y = fp_sqr_inline(y);
+  }
+  if (x.v[0] == 0x1234567u && y.v[3] == 7u) sink[0] = x.v[1];
+}
+
 // carry-linked rows only: 2 x (12-word mad.lo.cc/madc.hi.cc chain) per step, no reduction, no adds
 __global__ void __launch_bounds__(256) k_carry_row_peak(uint32_t seed, int iters, uint64_t* sink) {
   uint32_t e[12], o[12], x[12];
@@ -563,7 +576,8 @@ bls_ctx* bls_ctx_create(int device, int* err) {
   ctx->device = device;
   ctx->launches = 0;
   ctx->last_error[0] = 0;
-  if (cudaSetDevice(device) != cudaSuccess ||
+  DevGuard guard;
+  if (guard.enter(device) != cudaSuccess ||
       cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     if (err) *err = BLS_ERR_CUDA;
@@ -576,7 +590,8 @@ bls_ctx* bls_ctx_create(int device, int* err) {
 
 void bls_ctx_destroy(bls_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DevGuard guard;
+  guard.enter(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -628,7 +643,7 @@ int bls_internal_product_passes(bls_ctx* ctx, const uint64_t* in, size_t count, 
 
 int bls_fq12_product_dev(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq12* out1, void* scratch, void* stream) {
   if (!ctx || !out1 || (n && (!in || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   cudaStream_t s = pick(ctx, stream);
   if (n == 0) {   // empty product = one
     k_fq12_product<<<1, TPB, 0, s>>>((const uint64_t*)in, 0, (uint64_t*)out1, 1);
@@ -641,7 +656,7 @@ int bls_fq12_product_dev(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq12* o
 int bls_g1_wnaf_mul_dev(bls_ctx* ctx, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n, int window, void* stream) {
   if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   if (window <= 4) k_wnaf_mul_lazyk<Fp, false, BLS_WNAF_K, 8><<<blocks_for((n + BLS_WNAF_K - 1) / BLS_WNAF_K, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   else k_wnaf_mul_lazyk<Fp, false, 1, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   LAUNCH_CHECK();
@@ -650,7 +665,7 @@ int bls_g1_wnaf_mul_dev(bls_ctx* ctx, const bls_g1* bases, const bls_fr_repr* k,
 int bls_g2_wnaf_mul_dev(bls_ctx* ctx, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n, int window, void* stream) {
   if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   if (window <= 4) k_wnaf_mul_lazyk<Fp2, true, BLS_WNAF_K_G2, 8><<<blocks_for((n + BLS_WNAF_K_G2 - 1) / BLS_WNAF_K_G2, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   else k_wnaf_mul_lazyk<Fp2, true, 1, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
   LAUNCH_CHECK();
@@ -659,14 +674,14 @@ int bls_g2_wnaf_mul_dev(bls_ctx* ctx, const bls_g2* bases, const bls_fr_repr* k,
 
 int bls_g1_wnaf_table_dev(bls_ctx* ctx, const bls_g1* base, int window, bls_g1* table, void* stream) {
   if (!ctx || !base || !table || window < 2 || window > BLS_MAX_WNAF_FIXED_WINDOW) return BLS_ERR_INVALID_ARGUMENT;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   k_wnaf_table<Fp><<<1, 32, 0, pick(ctx, stream)>>>((const uint64_t*)base, (uint64_t*)table, window);
   LAUNCH_CHECK();
   return BLS_OK;
 }
 int bls_g2_wnaf_table_dev(bls_ctx* ctx, const bls_g2* base, int window, bls_g2* table, void* stream) {
   if (!ctx || !base || !table || window < 2 || window > BLS_MAX_WNAF_FIXED_WINDOW) return BLS_ERR_INVALID_ARGUMENT;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   k_wnaf_table<Fp2><<<1, 32, 0, pick(ctx, stream)>>>((const uint64_t*)base, (uint64_t*)table, window);
   LAUNCH_CHECK();
   return BLS_OK;
@@ -674,7 +689,7 @@ int bls_g2_wnaf_table_dev(bls_ctx* ctx, const bls_g2* base, int window, bls_g2* 
 int bls_g1_wnaf_fixed_base_dev(bls_ctx* ctx, const bls_g1* table, int window, const bls_fr_repr* k, bls_g1* out, size_t n, void* stream) {
   if (!ctx || window < 2 || window > BLS_MAX_WNAF_FIXED_WINDOW || (n && (!table || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   k_wnaf_fixed_base<Fp, 2><<<blocks_for((n + 1) / 2, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)table, window, (const uint64_t*)k, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
@@ -682,7 +697,7 @@ int bls_g1_wnaf_fixed_base_dev(bls_ctx* ctx, const bls_g1* table, int window, co
 int bls_g2_wnaf_fixed_base_dev(bls_ctx* ctx, const bls_g2* table, int window, const bls_fr_repr* k, bls_g2* out, size_t n, void* stream) {
   if (!ctx || window < 2 || window > BLS_MAX_WNAF_FIXED_WINDOW || (n && (!table || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   k_wnaf_fixed_base<Fp2, 2><<<blocks_for((n + 1) / 2, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)table, window, (const uint64_t*)k, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
@@ -703,7 +718,7 @@ size_t bls_batch_normalization_scratch_bytes(const bls_ctx* ctx, int degree, siz
 int bls_g1_batch_normalization_dev(bls_ctx* ctx, bls_g1* inout, size_t n, void* scratch, void* stream) {
   if (!ctx || (n && (!inout || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   size_t T = bn_threads(ctx, n);
   k_batch_normalization<Fp><<<(unsigned)(T / TPB), TPB, 0, pick(ctx, stream)>>>((uint64_t*)inout, n, (uint64_t*)scratch);
   LAUNCH_CHECK();
@@ -712,7 +727,7 @@ int bls_g1_batch_normalization_dev(bls_ctx* ctx, bls_g1* inout, size_t n, void* 
 int bls_g2_batch_normalization_dev(bls_ctx* ctx, bls_g2* inout, size_t n, void* scratch, void* stream) {
   if (!ctx || (n && (!inout || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   size_t T = bn_threads(ctx, n);
   k_batch_normalization<Fp2><<<(unsigned)(T / TPB), TPB, 0, pick(ctx, stream)>>>((uint64_t*)inout, n, (uint64_t*)scratch);
   LAUNCH_CHECK();
@@ -752,7 +767,7 @@ extern "C" {
 int bls_g2_prepare_batch(bls_ctx* ctx, const bls_g2_affine* q, bls_g2_prepared* out, size_t n) {
   if (!ctx || (n && (!q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   H2D(dq, q, n * sizeof(*q));
   DALLOC(dout, n * sizeof(*out));
   TRY(bls_g2_prepare_dev(ctx, (const bls_g2_affine*)dq.p, (bls_g2_prepared*)dout.p, n, nullptr));
@@ -764,7 +779,7 @@ int bls_g2_prepare_batch(bls_ctx* ctx, const bls_g2_affine* q, bls_g2_prepared* 
 static int miller_like(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, bool final_exp) {
   if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   H2D(dp, p, n * sizeof(*p));
   H2D(dq, q, n * sizeof(*q));
   DALLOC(dout, n * sizeof(*out));
@@ -780,7 +795,7 @@ int bls_pairing_batch(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine*
 int bls_miller_loop_prepared_batch(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q, bls_fq12* out, size_t n) {
   if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   H2D(dp, p, n * sizeof(*p));
   H2D(dq, q, n * sizeof(*q));
   DALLOC(dout, n * sizeof(*out));
@@ -793,7 +808,7 @@ int bls_miller_loop_prepared_batch(bls_ctx* ctx, const bls_g1_affine* p, const b
 static int shared_q_host(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q1, bls_fq12* out, size_t n, int final_exp) {
   if (!ctx || !q1 || (n && (!p || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   H2D(dp, p, n * sizeof(*p));
   H2D(dq, q1, sizeof(*q1));
   DALLOC(dout, n * sizeof(*out));
@@ -807,7 +822,7 @@ int bls_pairing_shared_q_batch(bls_ctx* ctx, const bls_g1_affine* p, const bls_g
 
 int bls_multi_miller_loop(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1) {
   if (!ctx || !out1 || (n && (!p || !q))) return BLS_ERR_INVALID_ARGUMENT;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   H2D(dp, p, n * sizeof(*p));
   H2D(dq, q, n * sizeof(*q));
   DALLOC(dscr, bls_multi_miller_scratch_bytes(ctx, n));
@@ -820,7 +835,7 @@ int bls_multi_miller_loop(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_aff
 
 int bls_multi_miller_loop_prepared(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q, size_t n, bls_fq12* out1) {
   if (!ctx || !out1 || (n && (!p || !q))) return BLS_ERR_INVALID_ARGUMENT;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   H2D(dp, p, n * sizeof(*p));
   H2D(dq, q, n * sizeof(*q));
   size_t T = bls_internal_mm_lane_pairs(ctx, n);
@@ -837,7 +852,7 @@ int bls_multi_miller_loop_prepared(bls_ctx* ctx, const bls_g1_affine* p, const b
 int bls_final_exponentiation_batch(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n) {
   if (!ctx || (n && (!in || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   H2D(din, in, n * sizeof(*in));
   DALLOC(dout, n * sizeof(*out));
   DALLOC(dok, n);
@@ -850,7 +865,7 @@ int bls_final_exponentiation_batch(bls_ctx* ctx, const bls_fq12* in, bls_fq12* o
 
 int bls_fq12_product(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq12* out1) {
   if (!ctx || !out1 || (n && !in)) return BLS_ERR_INVALID_ARGUMENT;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   H2D(din, in, n * sizeof(*in));
   DALLOC(dscr, bls_fq12_product_scratch_bytes(ctx, n));
   DALLOC(dout, sizeof(*out1));
@@ -863,7 +878,7 @@ int bls_fq12_product(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq12* out1)
 int bls_fq12_pow_batch(bls_ctx* ctx, const bls_fq12* a, const bls_fr_repr* k, bls_fq12* out, size_t n) {
   if (!ctx || (n && (!a || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   H2D(da, a, n * sizeof(*a));
   H2D(dk, k, n * sizeof(*k));
   DALLOC(dout, n * sizeof(*out));
@@ -876,7 +891,7 @@ int bls_fq12_pow_batch(bls_ctx* ctx, const bls_fq12* a, const bls_fr_repr* k, bl
 static int wnaf_host(bls_ctx* ctx, int degree, const void* bases, const bls_fr_repr* k, void* out, size_t n, int window, int mode) {
   if (!ctx || (n && (!bases || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
   H2D(db, bases, n * pb);
   H2D(dk, k, n * sizeof(*k));
@@ -909,7 +924,7 @@ int bls_g2_mul_batch(bls_ctx* ctx, const bls_g2* b, const bls_fr_repr* k, bls_g2
 // Wnaf::new().base(g, num_scalars).scalar(k_i): table built on the device, then every scalar against it
 static int wnaf_fixed_host(bls_ctx* ctx, int degree, const void* base, int window, const bls_fr_repr* k, void* out, size_t n, void* table_out) {
   if (!ctx || !base || window < 2 || window > BLS_MAX_WNAF_FIXED_WINDOW || (n && (!k || !out))) return BLS_ERR_INVALID_ARGUMENT;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
   size_t tsize = (size_t)1 << (window - 1);
   H2D(db, base, pb);
@@ -937,7 +952,7 @@ int bls_g2_wnaf_table(bls_ctx* ctx, const bls_g2* base, int window, bls_g2* tabl
 static int codec_host(bls_ctx* ctx, int degree, bool decode, const void* in, int compressed, int checked, void* out, uint8_t* status, size_t n) {
   if (!ctx || (n && (!in || !out || (decode && !status)))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   const size_t ab = degree == 2 ? sizeof(bls_g2_affine) : sizeof(bls_g1_affine);
   const size_t eb = (size_t)(degree == 2 ? 96 : 48) * (compressed ? 1 : 2);
   if (decode) {
@@ -969,7 +984,7 @@ int bls_g2_encode_batch(bls_ctx* ctx, const bls_g2_affine* in, int compressed, u
 static int from_x_host(bls_ctx* ctx, int degree, const void* x, const uint8_t* greatest, void* out, uint8_t* is_some, size_t n) {
   if (!ctx || (n && (!x || !greatest || !out || !is_some))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   const size_t xb = degree == 2 ? sizeof(bls_fq2) : sizeof(bls_fq);
   const size_t ab = degree == 2 ? sizeof(bls_g2_affine) : sizeof(bls_g1_affine);
   H2D(dx, x, n * xb);
@@ -990,7 +1005,7 @@ int bls_g2_point_from_x_batch(bls_ctx* ctx, const bls_fq2* x, const uint8_t* gre
 static int cofactor_host(bls_ctx* ctx, int degree, const void* in, void* out, size_t n) {
   if (!ctx || (n && (!in || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   const size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
   const size_t ab = degree == 2 ? sizeof(bls_g2_affine) : sizeof(bls_g1_affine);
   H2D(din, in, n * ab);
@@ -1008,7 +1023,7 @@ int bls_g2_scale_by_cofactor_batch(bls_ctx* ctx, const bls_g2_affine* in, bls_g2
 static int affine_mul_host(bls_ctx* ctx, int degree, const void* a, const bls_fr_repr* k, void* out, size_t n) {
   if (!ctx || (n && (!a || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   const size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
   const size_t ab = degree == 2 ? sizeof(bls_g2_affine) : sizeof(bls_g1_affine);
   H2D(da, a, n * ab);
@@ -1027,7 +1042,7 @@ int bls_g2_affine_mul_batch(bls_ctx* ctx, const bls_g2_affine* a, const bls_fr_r
 static int bn_host(bls_ctx* ctx, int degree, void* inout, size_t n) {
   if (!ctx || (n && !inout)) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
   H2D(dv, inout, n * pb);
   DALLOC(dscr, bls_batch_normalization_scratch_bytes(ctx, degree, n));
@@ -1043,7 +1058,7 @@ int bls_g2_batch_normalization(bls_ctx* ctx, bls_g2* inout, size_t n) { return b
 static int into_affine_host(bls_ctx* ctx, int degree, const void* in, void* out, size_t n) {
   if (!ctx || (n && (!in || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
   size_t ab = degree == 2 ? sizeof(bls_g2_affine) : sizeof(bls_g1_affine);
   H2D(din, in, n * pb);
@@ -1063,7 +1078,7 @@ static int pt_op_host(bls_ctx* ctx, int degree, int op, const void* a, const voi
   bool known = needs_b || op == BLS_PT_DOUBLE || op == BLS_PT_NEGATE;
   if (!ctx || !known || (n && (!a || !out || (needs_b && !b)))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
   size_t ab = degree == 2 ? sizeof(bls_g2_affine) : sizeof(bls_g1_affine);
   H2D(da, a, n * pb);
@@ -1101,7 +1116,7 @@ int bls_field_op_batch(bls_ctx* ctx, int degree, int op, const void* a, const vo
   }
   if (!valid || (binary && n && !b)) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   size_t eb = (size_t)degree * sizeof(bls_fq);
   H2D(da, a, n * eb);
   H2D(db, binary ? b : nullptr, binary ? n * eb : 1);
@@ -1128,7 +1143,7 @@ int bls_fr_op_batch(bls_ctx* ctx, int op, const bls_fr* a, const bls_fr* b, bls_
   const bool unary = op == BLS_OP_SQR || op == BLS_OP_NEG || op == BLS_OP_DBL || op == BLS_OP_INV || op == BLS_OP_FROM_REPR || op == BLS_OP_INTO_REPR;
   if ((!binary && !unary) || (binary && n && !b)) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   H2D(da, a, n * sizeof(*a));
   H2D(db, binary ? b : nullptr, binary ? n * sizeof(*b) : 1);
   DALLOC(dout, n * sizeof(*out));
@@ -1142,31 +1157,33 @@ int bls_fr_op_batch(bls_ctx* ctx, int op, const bls_fr* a, const bls_fr* b, bls_
 }
 
 int bls_imad_peak(bls_ctx* ctx, int variant, int iters, double* macs_per_s, double* ms_out) {
-  if (!ctx || !macs_per_s || iters <= 0 || variant < 0 || variant > 3) return BLS_ERR_INVALID_ARGUMENT;
-  CK(cudaSetDevice(ctx->device));
+  if (!ctx || !macs_per_s || iters <= 0 || variant < 0 || variant > 4) return BLS_ERR_INVALID_ARGUMENT;
+  USE_DEVICE(ctx);
   DALLOC(sink, 8);
   const int threads = 256;
   const unsigned blocks = (unsigned)ctx->sm_count * 8;   // 2048 threads per SM: full occupancy
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
+  struct Events {   // destroyed on every exit path, CK failures included
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Events() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+  } ev;
+  CK(cudaEventCreate(&ev.e0));
+  CK(cudaEventCreate(&ev.e1));
   float best = 1e30f;
   for (int rep = 0; rep < 4; rep++) {   // rep 0 is the warm-up
-    CK(cudaEventRecord(e0, ctx->stream));
+    CK(cudaEventRecord(ev.e0, ctx->stream));
     if (variant == 0) k_imad_wide_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, iters, (uint64_t*)sink.p);
     else if (variant == 1) k_fpmul_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, iters, (uint64_t*)sink.p);
     else if (variant == 3) k_carry_row_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, iters, (uint64_t*)sink.p);
+    else if (variant == 4) k_fpsqr_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, iters, (uint64_t*)sink.p);
     else k_imad32_peak<<<blocks, threads, 0, ctx->stream>>>(12345u, iters, (uint64_t*)sink.p);
     LAUNCH_CHECK();
-    CK(cudaEventRecord(e1, ctx->stream));
-    CK(cudaEventSynchronize(e1));
+    CK(cudaEventRecord(ev.e1, ctx->stream));
+    CK(cudaEventSynchronize(ev.e1));
     float ms = 0;
-    CK(cudaEventElapsedTime(&ms, e0, e1));
+    CK(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
     if (rep > 0 && ms < best) best = ms;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  double per_thread = variant == 1 ? 2.0 * 300.0 * iters : variant == 3 ? 8.0 * 24.0 * iters : (double)PEAK_CHAINS * PEAK_UNROLL * iters;
+  double per_thread = variant == 1 ? 2.0 * 300.0 * iters : variant == 4 ? 2.0 * 234.0 * iters : variant == 3 ? 8.0 * 24.0 * iters : (double)PEAK_CHAINS * PEAK_UNROLL * iters;
   double total = per_thread * threads * blocks;
   *macs_per_s = total / (best * 1e-3);
   if (ms_out) *ms_out = best;

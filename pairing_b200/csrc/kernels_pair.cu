@@ -29,6 +29,12 @@ __device__ __forceinline__ void st_p12(uint64_t* p, const P12& a) {
 #ifndef BLS_MM_MINB
 #define BLS_MM_MINB 2      /* blocks per SM of the multi-pairing kernels; 3 (168 registers) measured 3.22 vs 4.87 M pairs/s at 2^20 */
 #endif
+// BLS_PAIR_SMEM = 1 keeps the Miller accumulator f and the running G2 point R of every lane in shared memory (an odd
+// number of words per lane: conflict-free 32-bit accesses) instead of the per-thread stack.
+#ifndef BLS_PAIR_SMEM
+#define BLS_PAIR_SMEM 0
+#endif
+#define BLS_PAIR_SMEM_WORDS 109   /* P12 (72) + PJac (36) + 1 */
 template <bool FINAL_EXP>
 __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller(const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -40,8 +46,16 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller(con
   const bool live = pi[12] == 0 && qi[24] == 0;
   Fp px = ld_fp(pi), py = ld_fp(pi + 6);
   P2 qx = ld_p2(qi), qy = ld_p2(qi + 12);
+#if BLS_PAIR_SMEM
+  extern __shared__ uint32_t pair_smem[];
+  uint32_t* slot = pair_smem + BLS_PAIR_SMEM_WORDS * threadIdx.x;
+  P12& f = *reinterpret_cast<P12*>(slot);
+  PJac& r = *reinterpret_cast<PJac*>(slot + 72);
+  p_miller_loop_single(f, r, px, py, qx, qy);
+#else
   P12 f;
   p_miller_loop_single(f, px, py, qx, qy);
+#endif
   if (!live) p12_one(f);                       // mod.rs:49-54: skipped pair, f stays one
   if (FINAL_EXP) {
     P12 g;
@@ -50,6 +64,13 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller(con
   } else {
     if (active) st_p12(out + FQ12_W * i, f);
   }
+}
+static size_t pair_miller_smem_bytes() { return BLS_PAIR_SMEM ? (size_t)BLS_PAIR_SMEM_WORDS * 4 * BLS_PAIR_TPB : 0; }
+template <bool FE> static cudaError_t pair_miller_smem_optin() {
+  static bool done = false;      // per process; the attribute is per function and idempotent
+  if (done || !BLS_PAIR_SMEM) return cudaSuccess;
+  done = true;
+  return cudaFuncSetAttribute(k_pair_miller<FE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_miller_smem_bytes());
 }
 
 __device__ __forceinline__ void pcoeffs_set_one_if(bool dead, PCoeffs& c) {
@@ -347,7 +368,7 @@ extern "C" {
 int bls_g2_prepare_dev(bls_ctx* ctx, const bls_g2_affine* q, bls_g2_prepared* out, size_t n, void* stream) {
   if (!ctx || (n && (!q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   k_pair_g2_prepare<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
@@ -355,15 +376,16 @@ int bls_g2_prepare_dev(bls_ctx* ctx, const bls_g2_affine* q, bls_g2_prepared* ou
 int bls_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream) {
   if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
-  k_pair_miller<false><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  USE_DEVICE(ctx);
+  CK(pair_miller_smem_optin<false>());
+  k_pair_miller<false><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, pair_miller_smem_bytes(), pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
 }
 int bls_miller_loop_prepared_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q, bls_fq12* out, size_t n, void* stream) {
   if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   k_pair_miller_prepared<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
@@ -371,7 +393,7 @@ int bls_miller_loop_prepared_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls
 int bls_final_exponentiation_dev(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n, void* stream) {
   if (!ctx || (n && (!in || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   k_pair_final_exp<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)in, (uint64_t*)out, is_some, n);
   LAUNCH_CHECK();
   return BLS_OK;
@@ -379,8 +401,9 @@ int bls_final_exponentiation_dev(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out
 int bls_pairing_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream) {
   if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
-  k_pair_miller<true><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  USE_DEVICE(ctx);
+  CK(pair_miller_smem_optin<true>());
+  k_pair_miller<true><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, pair_miller_smem_bytes(), pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
 }
@@ -388,7 +411,7 @@ int bls_pairing_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q
 int bls_miller_loop_shared_q_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q1, bls_fq12* out, size_t n, int final_exp, void* stream) {
   if (!ctx || !q1 || (n && (!p || !out)) || ((uintptr_t)q1 & 15)) return BLS_ERR_INVALID_ARGUMENT;   // the bulk copy needs 16-byte alignment
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   if (final_exp) k_pair_miller_shared_q<true><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q1, (uint64_t*)out, n);
   else k_pair_miller_shared_q<false><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q1, (uint64_t*)out, n);
   LAUNCH_CHECK();
@@ -397,7 +420,7 @@ int bls_miller_loop_shared_q_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls
 int bls_fq12_pow_dev(bls_ctx* ctx, const bls_fq12* a, const bls_fr_repr* k, bls_fq12* out, size_t n, void* stream) {
   if (!ctx || (n && (!a || !k || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   k_pair_fq12_pow<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)a, (const uint64_t*)k, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
@@ -419,7 +442,7 @@ size_t bls_multi_miller_scratch_bytes(const bls_ctx* ctx, size_t n) {
 
 int bls_multi_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, void* scratch, void* stream) {
   if (!ctx || !out1 || (n && (!p || !q || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
-  CK(cudaSetDevice(ctx->device));
+  USE_DEVICE(ctx);
   cudaStream_t s = pick(ctx, stream);
   if (n == 0) {
     return bls_fq12_product_dev(ctx, nullptr, 0, out1, nullptr, stream);   // the empty product: one

@@ -345,9 +345,9 @@ static __device__ __noinline__ void p12_mul_by_line_pair(P12& f, const PLine& l,
 // mod.rs:40-102 for one pair, G2 steps on the fly
 // (no early exit for pairs with an infinity member: every lane must reach every shuffle; the
 // caller overwrites f with one for those pairs)
-__device__ __forceinline__ void p_miller_loop_single(P12& f, const Fp& px, const Fp& py, const P2& qx, const P2& qy) {
+__device__ __forceinline__ void p_miller_loop_single(P12& f, PJac& r, const Fp& px, const Fp& py, const P2& qx, const P2& qy) {
   p12_one(f);
-  PJac r; r.x = qx; r.y = qy; r.z = p2_one();
+  r.x = qx; r.y = qy; r.z = p2_one();
   PCoeffs c;
 #pragma unroll 1
   for (int b = BLS_LOOP_TOP; b >= 0; b--) {
@@ -362,6 +362,10 @@ __device__ __forceinline__ void p_miller_loop_single(P12& f, const Fp& px, const
   pg2_doubling_step(r, c);
   p_ell(f, c, px, py);
   p12_conjugate(f);
+}
+__device__ __forceinline__ void p_miller_loop_single(P12& f, const Fp& px, const Fp& py, const P2& qx, const P2& qy) {
+  PJac r;
+  p_miller_loop_single(f, r, px, py, qx, qy);
 }
 
 // exp_by_x (mod.rs:116-121): Field::pow(&[x]) (lib.rs:306-324) followed by a conjugation.  Two value-preserving

@@ -291,11 +291,11 @@ class Wnaf:
                 raise ValueError("Wnaf.base(g) without num_scalars needs a preceding .scalar(s)")
             return self._run(base, self._scalars, 0)
         w = Wnaf(self._curve, self._ctx)
-        w._base = base
         if base.ndim == 1:
             base = base.reshape(1, -1)
-        if base.shape[0] != 1:
+        if base.ndim != 2 or base.shape[0] != 1:
             raise ValueError("Wnaf.base(g, n) takes one base point")
+        w._base = base
         w._window = self._curve.recommended_wnaf_for_num_scalars(num_scalars)
         return w
 

@@ -111,3 +111,11 @@ def test_montgomery_product_is_carry_linked_imad_wide():
     h = _sass_histogram("k_fpmul_peak")
     wide = h["IMAD.WIDE.U32"] + h["IMAD.WIDE.U32.X"] + h["IMAD.HI.U32"]
     assert 2 * 288 <= wide <= 2 * 288 + 16, h
+
+
+def test_dedicated_squaring_is_222_wide_macs():
+    """fp_sqr (fq.rs:963-1016) is the generated 66 + 12 + 144 = 222 IMAD.WIDE.U32(.X) + 12 IMAD routine:
+    two independent squarings in the loop body of the measurement kernel"""
+    h = _sass_histogram("k_fpsqr_peak")
+    wide = h["IMAD.WIDE.U32"] + h["IMAD.WIDE.U32.X"] + h["IMAD.HI.U32"]
+    assert 2 * 222 <= wide <= 2 * 222 + 16, h

@@ -180,3 +180,13 @@ def test_line_pair_product_is_two_mul_by_014():
     cases.append((((one, zero, zero), (zero, zero, zero)), (r2(), r2(), r2()), (r2(), zero, r2())))
     for f, l, k in cases:
         assert line_pair(f, l, k) == m.fq12_mul_by_014(m.fq12_mul_by_014(f, *l), *k)
+
+
+def test_generated_squaring_schedule():
+    """tools/gen_fp_sqr.py --check: the committed fp_sqr_gen.cuh is what the generator emits, and the instruction
+    list replayed on integers squares correctly on [0, 2q], stays <= 2q and never drops a carry"""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_fp_sqr.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "222 wide MACs" in r.stdout

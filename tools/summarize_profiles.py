@@ -1,6 +1,6 @@
 """Turn the ncu outputs of a gpurun call (gpurun_out/) into the small tracked summaries under profiles/.
     python tools/summarize_profiles.py <launches.csv> <report.ncu-rep> <tag>"""
-import collections, csv, io, re, subprocess, sys
+import collections, csv, io, os, re, subprocess, sys
 
 launch_csv, rep, tag = sys.argv[1:4]
 out = []
@@ -42,7 +42,9 @@ keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+        "lts__t_sector_hit_rate.pct", "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum", "launch__shared_mem_per_block_dynamic", "launch__shared_mem_per_block_static",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum", "launch__stack_size"]
 for r in rr[2:]:
     d = dict(zip(h, r))
     out.append("## `ncu --set full` of `%s`, %s" % (d["Kernel Name"][:80], rep))
@@ -84,5 +86,5 @@ out.append("|---|---|")
 for k, v in stall.most_common(8):
     out.append("| %s | %.2f %% |" % (k, 100 * v / T))
 out.append("")
-open("profiles/%s.md" % tag, "w").write("# ncu summary %s\n\n" % tag + "\n".join(out) + "\n")
+open(os.path.join(os.environ.get("PROFILE_OUT_DIR", "profiles"), "%s.md" % tag), "w").write("# ncu summary %s\n\n" % tag + "\n".join(out) + "\n")
 print("\n".join(out))
