@@ -49,8 +49,9 @@ def parse():
     ap.add_argument("--mm-log2", type=int, default=20)
     ap.add_argument("--wnaf-log2", type=int, default=24)
     ap.add_argument("--g2-log2", type=int, default=20)
-    ap.add_argument("--prep-log2", type=int, default=18)
+    ap.add_argument("--prep-log2", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mgpu", action="store_true")
     return ap.parse_args()
 
 
@@ -73,6 +74,49 @@ def cpu_pairings_per_s(sample, threads):
     o.pairing(p, q, threads)
     dt = time.perf_counter() - t0
     return sample / dt, dt
+
+
+def cpu_secondary_baselines(threads, budget_s=3.0):
+    """The reference's CPU algorithm (C restatement, all host threads) on bounded samples of BASELINE configs[2..4]:
+    multi-Miller pairs/s, G1 wNAF + normalisation muls/s, G2 wNAF + normalisation + G2Prepared muls/s."""
+    sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+    import datagen as dg
+    import oracle_lib as o
+    out = {}
+
+    def sized(fn, unit_probe):
+        """run fn(n) on a probe, then once more on a sample sized for ~budget_s of wall clock"""
+        t0 = time.perf_counter(); fn(unit_probe); dt = time.perf_counter() - t0
+        n = max(unit_probe, int(unit_probe * budget_s / max(dt, 1e-3)))
+        t0 = time.perf_counter(); fn(n); dt = time.perf_counter() - t0
+        return n, dt
+
+    p, q = oracle_inputs(256)
+    def mm(n):
+        reps = (n + 255) // 256
+        o.multi_miller_product(__import__("numpy").tile(p, (reps, 1))[:n], __import__("numpy").tile(q, (reps, 1))[:n], threads)
+    n, dt = sized(mm, threads * 16)
+    out["multi_miller_loop"] = {"value": n / dt, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                "sample": "product of %d pairs in %.1f s (per-thread partial products, oracle/bls_oracle.c)" % (n, dt)}
+    b1, k = dg.g1_points(256, 303), dg.rand_scalars(256, 304, edge_cases=False)
+    import numpy as np
+    def g1(n):
+        reps = (n + 255) // 256
+        r = o.g1_op("wnaf", np.tile(b1, (reps, 1))[:n], k=np.tile(k, (reps, 1))[:n], threads=threads)
+        o.g1_batch_normalization(r)
+    n, dt = sized(g1, threads * 64)
+    out["g1_wnaf_mul"] = {"value": n / dt, "unit": "scalar-muls/s", "cores": threads, "kind": "port",
+                          "sample": "%d G1 wNAF multiplications (threaded) + batch_normalization (one thread, as in the crate) in %.1f s" % (n, dt)}
+    b2 = dg.g2_points(128, 305)
+    def g2(n):
+        reps = (n + 127) // 128
+        r = o.g2_op("wnaf", np.tile(b2, (reps, 1))[:n], k=np.tile(k[:128], (reps, 1))[:n], threads=threads)
+        o.g2_batch_normalization(r)
+        o.g2_prepare(o.g2_into_affine(r), threads)
+    n, dt = sized(g2, threads * 16)
+    out["g2_wnaf_mul_prepare"] = {"value": n / dt, "unit": "scalar-muls/s", "cores": threads, "kind": "port",
+                                  "sample": "%d G2 wNAF multiplications + batch_normalization + G2Prepared in %.1f s" % (n, dt)}
+    return out
 
 
 def run_reference(args):
@@ -326,22 +370,42 @@ def run_ours(args):
         ms_k, _ = timed(lambda: eng.pairing(pa[:1000].contiguous(), qa[:1000].contiguous(), k_out))
         secondary["single_pairing"] = {"latency_ms": ms_one, "batch_1000_ms": ms_k, "value": world * 1000 / (ms_k * 1e-3), "unit": "pairings/s",
                                        "units_per_gpu": 1000, "ms": ms_k, "roofline_frac": 1000 / (ms_k * 1e-3) * MAC32_PER_PAIRING / peak_macs,
-                                       "config": "configs[0]: one pairing (latency-bound: one lane pair of one warp) and 1000 pairings as in bench_pairing_full"}
+                                       "config": "configs[0]: one pairing and the 1000 pairings of bench_pairing_full, on the warp-cooperative kernel (one WARP per pairing)"}
         from pairing_b200 import dist as pdist
-        # configs[2]: multi_miller_loop product of 2^20 pairs per GPU + ONE shared final exponentiation
+        # configs[2] as stated: ONE multi_miller_loop product of 2^20 pairs IN TOTAL, sharded over the ranks (strong scaling),
+        # with one shared final exponentiation.  Per rank: Miller kernel (one partial per block) + fold to one 576-byte
+        # partial; all-gather (NCCL); fold of the `world` partials + the final exponentiation on the warp-cooperative engine.
         nm = 1 << args.mm_log2
-        pm, qm = tile(pa, nm), tile(qa, nm)
-        pdist.multi_miller_loop_sharded(eng.multi_miller_loop, eng.fq12_product, pm[:4096].contiguous(), qm[:4096].contiguous())
-        eng._buf("mm", ctx.multi_miller_scratch_bytes(nm))          # grow-only scratch sized before the timed pass
+        lo, hi = pdist.shard_range(nm, rank, world)
+        pm, qm = tile(pa, hi - lo), tile(qa, hi - lo)
+        pdist.pairing_product_sharded(eng, pm[:4096].contiguous(), qm[:4096].contiguous())
+        eng._buf("mm", ctx.multi_miller_scratch_bytes(hi - lo))     # grow-only scratch sized before the timed passes
         def mm_run():
-            mm = pdist.multi_miller_loop_sharded(eng.multi_miller_loop, eng.fq12_product, pm, qm)
-            return eng.final_exponentiation(mm)[0]
+            return pdist.pairing_product_sharded(eng, pm, qm)[0]
         mm_run()                                                    # one untimed full-size pass, then the mean of three
         ms3, fe = timed(lambda: [mm_run() for _ in range(3)][-1])
         ms = ms3 / 3
-        secondary["multi_miller_loop"] = entry(nm, ms, MAC32_PER_MM_PAIR, unit="pairs/s", passes=3,
-                                               collective="all_gather of one 576-byte Fq12 per rank (NCCL)" if world > 1 else "none (1 rank)",
-                                               config="configs[2]: product of 2^%d pairs per GPU, one final exponentiation" % args.mm_log2)
+        # the same product once more with an event after every phase (this rank's times; max over ranks below)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        barrier()
+        ev[0].record()
+        part = eng.multi_miller_loop(pm, qm)
+        ev[1].record()
+        allp = pdist.all_gather_partials(part) if world > 1 else part
+        ev[2].record()
+        fe2, ok2 = eng.fq12_product_tail(allp, final_exp=True)
+        ev[3].record()
+        barrier()
+        phases = [max_over_ranks(ev[i].elapsed_time(ev[i + 1])) for i in range(3)]
+        assert bool(torch.equal(fe, fe2)) and int(ok2.item()) == 1
+        rate = nm / (ms * 1e-3)
+        secondary["multi_miller_loop"] = {
+            "value": rate, "unit": "pairs/s", "pairs_total": nm, "pairs_per_gpu": hi - lo, "ms": ms, "passes": 3, "scaling": "strong",
+            "roofline_frac": rate / world * MAC32_PER_MM_PAIR / peak_macs,
+            "phase_ms": {"miller_and_fold_per_gpu": phases[0], "all_gather": phases[1], "fold_and_final_exponentiation": phases[2]},
+            "collective": "all_gather of one 576-byte Fq12 per rank (NCCL)" if world > 1 else "none (1 rank)",
+            "gt_checksum": int(fe.cpu().numpy().view(np.uint64).sum(dtype=np.uint64)) & 0xFFFFFFFF,
+            "config": "configs[2]: ONE product of 2^%d pairs sharded over %d GPU(s) + one final exponentiation" % (args.mm_log2, world)}
         del pm, qm
         # configs[3]: G1 wNAF scalar multiplication of 2^24 points per GPU + batch affine normalisation
         nw = 1 << args.wnaf_log2
@@ -367,7 +431,7 @@ def run_ours(args):
         ms_norm, _ = timed(lambda: eng.g2_batch_normalization_(w2))
         aff2 = eng.jacobian_to_affine_rows(w2, 12)
         del b2, k2, w2
-        npre = min(n2, 1 << args.prep_log2)
+        npre = min(n2, 1 << args.prep_log2)                         # default: all 2^20 points (20.5 GB of coefficients)
         prep = torch.empty((npre, 68 * 36 + 1), dtype=torch.int64, device=eng.device)
         eng.g2_prepare(aff2[:4096].contiguous(), prep[:4096])
         ms_prep, _ = timed(lambda: eng.g2_prepare(aff2[:npre], prep))
@@ -403,10 +467,49 @@ def run_ours(args):
         secondary["gt_pow"] = entry(npow, ms_pow, (254 * 36 + 127 * 54) * 300, unit="powers/s",
                                     config="SURVEY 8f-4: Fq12::pow(FrRepr) for 2^14 GT elements per GPU")
 
+    # host copies for the single-process multi-device measurement below (rank 0 only)
+    mg_host = None
+    if rank == 0 and not args.no_secondary and not args.no_mgpu:
+        nm = 1 << args.mm_log2
+        reps = (nm + n - 1) // n
+        mg_host = (torch.empty((nm, pa.shape[1]), dtype=torch.int64).pin_memory(), torch.empty((nm, qa.shape[1]), dtype=torch.int64).pin_memory())
+        mg_host[0].copy_(pa.cpu().repeat(reps, 1)[:nm]); mg_host[1].copy_(qa.cpu().repeat(reps, 1)[:nm])
+
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return 0
+
+    # ---- configs[2] through the C ABI a Rust / C caller binds: ONE process, ONE call, all `world` devices
+    # (bls_mgpu_pairing_product: host buffers in, one GT element out; H2D, per-device Miller kernels, peer-copy gather,
+    # fold + final exponentiation inside the call).  The other ranks have left; their devices are idle.
+    if mg_host is not None:
+        import pairing_b200._native as nat
+        if world > 1:
+            time.sleep(2.0)                                         # let the other ranks' processes tear down
+        try:
+            with nat.MultiGpu(world) as mg:
+                nm = mg_host[0].shape[0]
+                lib = mg._lib
+                gt = np.zeros((1, 72), dtype=np.uint64); ok = np.zeros(1, dtype=np.uint8)
+                def mg_run():
+                    rc = lib.bls_mgpu_pairing_product(mg._m, mg_host[0].data_ptr(), mg_host[1].data_ptr(), nm, gt.ctypes.data, ok.ctypes.data)
+                    if rc != 0:
+                        raise RuntimeError("bls_mgpu_pairing_product failed: %d" % rc)
+                mg_run()
+                best, phases = None, None
+                for _ in range(3):
+                    t0 = time.perf_counter(); mg_run(); dt = time.perf_counter() - t0
+                    if best is None or dt < best:
+                        best, phases = dt, mg.last_phase_ms()
+                secondary["multi_miller_loop"]["e2e_c_abi"] = {
+                    "value": nm / best, "unit": "pairs/s", "ms": best * 1e3, "devices": world, "api": "bls_mgpu_pairing_product (one process, host buffers, pinned)",
+                    "h2d_bytes": nm * (104 + 200), "d2h_bytes": 577, "phase_ms": phases, "is_some": int(ok[0]),
+                    "gt_checksum": int(gt.sum(dtype=np.uint64)) & 0xFFFFFFFF}
+        except Exception as e:                                      # reported, never fatal for the headline line
+            secondary["multi_miller_loop"]["e2e_c_abi"] = {"error": str(e)[:200]}
 
     # ---- CPU baseline on the host cores (bounded sample)
     cpu = None
@@ -417,6 +520,10 @@ def run_ours(args):
         rate, dt = cpu_pairings_per_s(sample, threads)
         cpu = {"value": rate, "unit": "pairings/s", "cores": threads, "kind": "port",
                "sample": "%d full pairings of the same workload in %.1f s, C restatement of the reference (oracle/bls_oracle.c), %d pthreads" % (sample, dt, threads)}
+        if secondary:
+            for key, base in cpu_secondary_baselines(threads).items():
+                if key in secondary:
+                    secondary[key]["cpu_baseline"] = base
 
     traffic = None                                                  # dram bytes per launch of the dominant kernel, from the committed ncu capture
     try:
@@ -451,8 +558,6 @@ def run_ours(args):
         "secondary": secondary,
     }
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 

@@ -64,6 +64,11 @@ int bls_ctx_device(const bls_ctx* ctx);
 int bls_ctx_sm_count(const bls_ctx* ctx);
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
 uint64_t bls_ctx_launch_count(const bls_ctx* ctx);
+/* bls_pairing_* / bls_final_exponentiation_* pick between two kernels by batch size: up to these many elements one WARP
+ * works on each element (latency path: ~2 ms for one pairing or for a thousand, the crate's bench_pairing_full shape),
+ * above them one lane pair does (throughput path: 9.9 ms of latency, 1.37 M pairings/s).  Same bits either way.
+ * 0 disables the latency path.  Defaults: 4096 / 4096. */
+int bls_ctx_set_latency_path_limits(bls_ctx*, size_t max_pairings, size_t max_final_exps);
 
 /* ------------------------------------------------------------------ pairing engine (host buffers) */
 
@@ -82,6 +87,10 @@ int bls_pairing_shared_q_batch(bls_ctx*, const bls_g1_affine* p, const bls_g2_pr
 /* ONE Engine::miller_loop over n pairs: the product of the n Miller values (mod.rs:80-95). */
 int bls_multi_miller_loop(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1);
 int bls_multi_miller_loop_prepared(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q, size_t n, bls_fq12* out1);
+/* Engine::final_exponentiation(&Engine::miller_loop(pairs)) in ONE call -- the batch-verification shape (BASELINE
+ * configs[2]): the Miller kernel leaves one partial product per block, one tail kernel folds them and runs the single
+ * final exponentiation on the warp-cooperative engine.  *is_some = 0 marks the reference's None (product 0). */
+int bls_pairing_product(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, uint8_t* is_some);
 /* Engine::final_exponentiation, mod.rs:104-160; is_some[i] = 0 marks the reference's None (input 0),
  * in which case out[i] is all-zero.  is_some may be NULL. */
 int bls_final_exponentiation_batch(bls_ctx*, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n);
@@ -166,9 +175,17 @@ enum {
   BLS_OP_MUL_BY_014 = 14, /* Fq12 only: sparse operands b.c0.c0, b.c0.c1, b.c1.c1 (fq12.rs:34-48) */
   BLS_OP_MUL_BY_01 = 15,  /* Fq6 only: b.c0, b.c1 (fq6.rs:68-109) */
   BLS_OP_MUL_BY_1 = 16,   /* Fq6 only: b.c1 (fq6.rs:40-66) */
-  BLS_OP_SQRT = 17        /* Fq, Fq2: SqrtField::sqrt (fq.rs:1147-1170, fq2.rs:167-221); ok = 0 for a non-residue */
+  BLS_OP_SQRT = 17,       /* Fq, Fq2: SqrtField::sqrt (fq.rs:1147-1170, fq2.rs:167-221); ok = 0 for a non-residue */
+  /* lane-pair tower only (bls_pair_field_op_batch): */
+  BLS_OP_MUL_BY_LINE_PAIR = 18,  /* Fq12: a * l * m for two sparse lines packed in b as (l.c0, l.c1, l.c4, m.c0, m.c1, m.c4) */
+  BLS_OP_CYCLOTOMIC_SQR = 19     /* Fq12: Granger-Scott squaring; equals `square` for elements of the cyclotomic subgroup */
 };
 int bls_field_op_batch(bls_ctx*, int degree, int op, const void* a, const void* b, void* out, uint8_t* ok, size_t n);
+/* The same element-wise operations (degree 2, 6, 12) on the LANE-PAIR tower the pairing kernels run (two lanes per element,
+ * lazily reduced dual products): a separate implementation of fq2.rs / fq6.rs / fq12.rs, so it gets its own parity entry.
+ * Operands may be any representative in [0, 2q]; results are canonical. */
+int bls_pair_field_op_batch(bls_ctx*, int degree, int op, const void* a, const void* b, void* out, uint8_t* ok, size_t n);
+int bls_pair_field_op_dev(bls_ctx*, int degree, int op, const void* a, const void* b, void* out, uint8_t* ok, size_t n, void* stream);
 
 /* The scalar field Fr (fr.rs:324-572), element-wise: op is BLS_OP_ADD / SUB / MUL / SQR / NEG / DBL / INV /
  * FROM_REPR (bls_fr_repr -> bls_fr; ok = 0 for values >= r) / INTO_REPR (bls_fr -> bls_fr_repr).  The step after the
@@ -191,6 +208,11 @@ int bls_fq12_pow_dev(bls_ctx*, const bls_fq12* a, const bls_fr_repr* k, bls_fq12
 /* scratch: bls_multi_miller_scratch_bytes(ctx, n) bytes */
 size_t bls_multi_miller_scratch_bytes(const bls_ctx*, size_t n);
 int bls_multi_miller_loop_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, void* scratch, void* stream);
+int bls_pairing_product_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, uint8_t* is_some, void* scratch, void* stream);
+/* product of n Fq12 values by ONE block (n up to a few thousand: the per-block or per-device partials of a sharded
+ * multi_miller_loop), then -- final_exp != 0 -- Engine::final_exponentiation of the product (mod.rs:104-160) on the
+ * warp-cooperative engine.  No scratch.  is_some (device pointer, may be NULL) as in bls_final_exponentiation_dev. */
+int bls_fq12_product_tail_dev(bls_ctx*, const bls_fq12* in, size_t n, bls_fq12* out1, int final_exp, uint8_t* is_some, void* stream);
 size_t bls_fq12_product_scratch_bytes(const bls_ctx*, size_t n);
 int bls_fq12_product_dev(bls_ctx*, const bls_fq12* in, size_t n, bls_fq12* out1, void* scratch, void* stream);
 int bls_g1_wnaf_mul_dev(bls_ctx*, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n, int window, void* stream);
@@ -204,6 +226,27 @@ int bls_g2_wnaf_fixed_base_dev(bls_ctx*, const bls_g2* table, int window, const 
 size_t bls_batch_normalization_scratch_bytes(const bls_ctx*, int degree, size_t n);
 int bls_g1_batch_normalization_dev(bls_ctx*, bls_g1* inout, size_t n, void* scratch, void* stream);
 int bls_g2_batch_normalization_dev(bls_ctx*, bls_g2* inout, size_t n, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------ several GPUs behind ONE call
+ * Engine::miller_loop takes ALL pairs of a product in one call (mod.rs:40-102), and a Rust / C caller is one process.
+ * A bls_mgpu binds n devices of one node.  An n-pair product is split into contiguous shards, one host thread per
+ * device; every device reduces its shard to ONE 576-byte partial product, the partials travel to the first device by
+ * peer copies (NVLink; staged through the host where peer access is unavailable), and the first device folds them and
+ * runs the single final exponentiation.  Independent batches (pairings, wNAF multiplications) are sharded the same
+ * way with no exchange step.  devices == NULL selects devices 0 .. n_devices-1. */
+typedef struct bls_mgpu bls_mgpu;
+bls_mgpu* bls_mgpu_create(const int* devices, int n_devices, int* err);
+void bls_mgpu_destroy(bls_mgpu*);
+int bls_mgpu_device_count(const bls_mgpu*);
+bls_ctx* bls_mgpu_ctx(bls_mgpu*, int i);   /* the single-device context of shard i (owned by the bls_mgpu) */
+int bls_mgpu_multi_miller_loop(bls_mgpu*, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1);
+int bls_mgpu_pairing_product(bls_mgpu*, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, uint8_t* is_some);
+int bls_mgpu_pairing_batch(bls_mgpu*, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n);
+int bls_mgpu_g1_wnaf_mul_batch(bls_mgpu*, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n);
+int bls_mgpu_g2_wnaf_mul_batch(bls_mgpu*, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n);
+/* host wall-clock phases of the last product call, milliseconds: ms3[0] = shards (H2D + Miller kernel + per-device
+ * fold + peer copy, slowest device), ms3[1] = fold of the partials + final exponentiation + D2H, ms3[2] = whole call */
+int bls_mgpu_last_phase_ms(const bls_mgpu*, double* ms3);
 
 /* ------------------------------------------------------------------ measurement
  * Register-resident integer-multiply microbenchmark: the roofline denominator for this path

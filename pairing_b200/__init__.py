@@ -15,10 +15,10 @@ include/pairing_b200.h (one row per element), because the point of the GPU path 
 arithmetic runs in the CUDA library (pairing_b200/lib/libpairing_b200.so); there is no CPU
 fallback, and importing this package never touches the oracle.
 """
-from ._native import (BlsError, Context, LIB_PATH, SYMBOLS, W_FQ, W_FQ2, W_FQ6, W_FQ12, W_FR, W_G1,  # noqa: F401
+from ._native import (BlsError, Context, MultiGpu, LIB_PATH, SYMBOLS, W_FQ, W_FQ2, W_FQ6, W_FQ12, W_FR, W_G1,  # noqa: F401
                       W_G1A, W_G2, W_G2A, W_G2P, load)
 from .engine import (Bls12, G1, G1Affine, G1Compressed, G1Uncompressed, G2, G2Affine, G2Compressed, G2Prepared,  # noqa: F401
                      G2Uncompressed, Wnaf, default_context)
 
 __all__ = ["Bls12", "G1", "G2", "G1Affine", "G2Affine", "G2Prepared", "Wnaf", "G1Compressed", "G1Uncompressed",
-           "G2Compressed", "G2Uncompressed", "Context", "BlsError", "default_context", "load"]
+           "G2Compressed", "G2Uncompressed", "Context", "MultiGpu", "BlsError", "default_context", "load"]

@@ -17,13 +17,14 @@ W_FQ, W_FQ2, W_FQ6, W_FQ12 = 6, 12, 36, 72
 W_G1A, W_G1, W_G2A, W_G2, W_FR, W_G2P = 13, 18, 25, 36, 4, 68 * 3 * 12 + 1
 
 OPS = dict(add=0, sub=1, mul=2, sqr=3, neg=4, dbl=5, inv=6, from_repr=7, into_repr=8, mul_nonres=9,
-           frob1=10, frob2=11, frob3=12, conj=13, mul_by_014=14, mul_by_01=15, mul_by_1=16, sqrt=17)
+           frob1=10, frob2=11, frob3=12, conj=13, mul_by_014=14, mul_by_01=15, mul_by_1=16, sqrt=17,
+           mul_by_line_pair=18, cyclotomic_sqr=19)
 PT_OPS = dict(double=0, add=1, add_mixed=2, negate=3, sub=6)
 
 # every symbol include/pairing_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "bls_ctx_create", "bls_ctx_destroy", "bls_strerror", "bls_ctx_last_error", "bls_ctx_device",
-    "bls_ctx_sm_count", "bls_ctx_launch_count",
+    "bls_ctx_sm_count", "bls_ctx_launch_count", "bls_ctx_set_latency_path_limits",
     "bls_g2_prepare_batch", "bls_miller_loop_batch", "bls_miller_loop_prepared_batch",
     "bls_multi_miller_loop", "bls_multi_miller_loop_prepared", "bls_final_exponentiation_batch",
     "bls_pairing_batch", "bls_fq12_product",
@@ -43,6 +44,11 @@ SYMBOLS = [
     "bls_g1_point_from_x_batch", "bls_g2_point_from_x_batch", "bls_g1_scale_by_cofactor_batch", "bls_g2_scale_by_cofactor_batch",
     "bls_g1_decode_batch", "bls_g2_decode_batch", "bls_g1_encode_batch", "bls_g2_encode_batch",
     "bls_g1_wnaf_table_dev", "bls_g2_wnaf_table_dev", "bls_g1_wnaf_fixed_base_dev", "bls_g2_wnaf_fixed_base_dev",
+    "bls_pairing_product", "bls_pairing_product_dev", "bls_fq12_product_tail_dev",
+    "bls_pair_field_op_batch", "bls_pair_field_op_dev",
+    "bls_mgpu_create", "bls_mgpu_destroy", "bls_mgpu_device_count", "bls_mgpu_ctx", "bls_mgpu_multi_miller_loop",
+    "bls_mgpu_pairing_product", "bls_mgpu_pairing_batch", "bls_mgpu_g1_wnaf_mul_batch", "bls_mgpu_g2_wnaf_mul_batch",
+    "bls_mgpu_last_phase_ms",
 ]
 
 
@@ -75,6 +81,7 @@ def load():
     lib.bls_ctx_sm_count.argtypes = [vp]
     lib.bls_ctx_launch_count.restype = ctypes.c_uint64
     lib.bls_ctx_launch_count.argtypes = [vp]
+    lib.bls_ctx_set_latency_path_limits.argtypes = [vp, sz, sz]
     for name in ("bls_multi_miller_scratch_bytes", "bls_fq12_product_scratch_bytes"):
         getattr(lib, name).restype = sz
         getattr(lib, name).argtypes = [vp, sz]
@@ -138,7 +145,25 @@ def load():
         "bls_g1_batch_normalization_dev": [vp, vp, sz, vp, vp],
         "bls_g2_batch_normalization_dev": [vp, vp, sz, vp, vp],
         "bls_imad_peak": [vp, ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
+        "bls_pairing_product": [vp, vp, vp, sz, vp, vp],
+        "bls_pair_field_op_batch": [vp, ci, ci, vp, vp, vp, vp, sz],
+        "bls_pair_field_op_dev": [vp, ci, ci, vp, vp, vp, vp, sz, vp],
+        "bls_pairing_product_dev": [vp, vp, vp, sz, vp, vp, vp, vp],
+        "bls_fq12_product_tail_dev": [vp, vp, sz, vp, ci, vp, vp],
+        "bls_mgpu_multi_miller_loop": [vp, vp, vp, sz, vp],
+        "bls_mgpu_pairing_product": [vp, vp, vp, sz, vp, vp],
+        "bls_mgpu_pairing_batch": [vp, vp, vp, vp, sz],
+        "bls_mgpu_g1_wnaf_mul_batch": [vp, vp, vp, vp, sz],
+        "bls_mgpu_g2_wnaf_mul_batch": [vp, vp, vp, vp, sz],
+        "bls_mgpu_last_phase_ms": [vp, ctypes.POINTER(ctypes.c_double)],
     }
+    lib.bls_mgpu_create.restype = vp
+    lib.bls_mgpu_create.argtypes = [ctypes.POINTER(ci), ci, ctypes.POINTER(ci)]
+    lib.bls_mgpu_destroy.restype = None
+    lib.bls_mgpu_destroy.argtypes = [vp]
+    lib.bls_mgpu_device_count.argtypes = [vp]
+    lib.bls_mgpu_ctx.restype = vp
+    lib.bls_mgpu_ctx.argtypes = [vp, ci]
     for name, args in sig.items():
         fn = getattr(lib, name)
         fn.argtypes = args
@@ -200,6 +225,10 @@ class Context:
     def launch_count(self):
         return int(self._lib.bls_ctx_launch_count(self._ctx))
 
+    def set_latency_path_limits(self, max_pairings, max_final_exps):
+        """Batch sizes up to which pairing / final_exponentiation run one WARP per element (0: lane-pair kernels always)."""
+        self._check(self._lib.bls_ctx_set_latency_path_limits(self._ctx, int(max_pairings), int(max_final_exps)))
+
     # ------------------------------------------------------------------ engine, host arrays
     def g2_prepare(self, q):
         q = _arr(q, W_G2A, "q")
@@ -252,6 +281,16 @@ class Context:
 
     def multi_miller_loop_prepared(self, p, qp):
         return self._multi(self._lib.bls_multi_miller_loop_prepared, p, qp, W_G2P)
+
+    def pairing_product(self, p, q):
+        """final_exponentiation(miller_loop(all pairs)) in one call -> ((1, 72) GT element, is_some)."""
+        p, q = _arr(p, W_G1A, "p"), _arr(q, W_G2A, "q")
+        if p.shape[0] != q.shape[0]:
+            raise ValueError("p and q must have the same length")
+        out = np.zeros((1, W_FQ12), dtype=np.uint64)
+        ok = np.zeros(1, dtype=np.uint8)
+        self._check(self._lib.bls_pairing_product(self._ctx, _p(p), _p(q), p.shape[0], _p(out), _p(ok)))
+        return out, bool(ok[0])
 
     def final_exponentiation(self, f):
         f = _arr(f, W_FQ12, "f")
@@ -395,6 +434,18 @@ class Context:
         self._check(self._lib.bls_field_op_batch(self._ctx, degree, OPS[op], _p(a), _p(b), _p(out), _p(ok), a.shape[0]))
         return out, ok
 
+    def pair_field_op(self, degree, op, a, b=None):
+        """the same operation on the lane-pair tower of the pairing kernels (degree 2, 6, 12)"""
+        a = _arr(a, 6 * degree, "a")
+        if b is not None:
+            b = _arr(b, 6 * degree, "b")
+            if b.shape[0] != a.shape[0]:
+                raise ValueError("a and b must have the same length")
+        out = np.zeros_like(a)
+        ok = np.zeros(a.shape[0], dtype=np.uint8)
+        self._check(self._lib.bls_pair_field_op_batch(self._ctx, degree, OPS[op], _p(a), _p(b), _p(out), _p(ok), a.shape[0]))
+        return out, ok
+
     # ------------------------------------------------------------------ device pointers
     def point_from_x(self, g2, x, greatest):
         """$affine::get_point_from_x for n x-coordinates (Montgomery limbs) -> (affine rows, is_some)."""
@@ -452,3 +503,88 @@ class Context:
         macs, ms = ctypes.c_double(0), ctypes.c_double(0)
         self._check(self._lib.bls_imad_peak(self._ctx, variant, iters, ctypes.byref(macs), ctypes.byref(ms)))
         return macs.value, ms.value
+
+
+class MultiGpu:
+    """Several devices of one node behind one call (bls_mgpu): an n-pair product or batch is split into contiguous
+    shards, one host thread per device inside the library; the product's 576-byte partials meet on the first device."""
+
+    def __init__(self, devices):
+        self._lib = load()
+        devices = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+        arr = (ctypes.c_int * len(devices))(*devices)
+        err = ctypes.c_int(0)
+        self._m = self._lib.bls_mgpu_create(arr, len(devices), ctypes.byref(err))
+        if not self._m:
+            raise BlsError("bls_mgpu_create(%r) failed: %s" % (devices, self._lib.bls_strerror(err.value).decode()))
+        self.devices = devices
+
+    def close(self):
+        if getattr(self, "_m", None):
+            self._lib.bls_mgpu_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            msgs = [self._lib.bls_ctx_last_error(self._lib.bls_mgpu_ctx(self._m, i)).decode() for i in range(len(self.devices))]
+            raise BlsError("%s %r" % (self._lib.bls_strerror(rc).decode(), [m for m in msgs if m]))
+
+    @property
+    def device_count(self):
+        return self._lib.bls_mgpu_device_count(self._m)
+
+    def _pairs(self, p, q):
+        p, q = _arr(p, W_G1A, "p"), _arr(q, W_G2A, "q")
+        if p.shape[0] != q.shape[0]:
+            raise ValueError("p and q must have the same length")
+        return p, q
+
+    def multi_miller_loop(self, p, q):
+        p, q = self._pairs(p, q)
+        out = np.zeros((1, W_FQ12), dtype=np.uint64)
+        self._check(self._lib.bls_mgpu_multi_miller_loop(self._m, _p(p), _p(q), p.shape[0], _p(out)))
+        return out
+
+    def pairing_product(self, p, q):
+        p, q = self._pairs(p, q)
+        out = np.zeros((1, W_FQ12), dtype=np.uint64)
+        ok = np.zeros(1, dtype=np.uint8)
+        self._check(self._lib.bls_mgpu_pairing_product(self._m, _p(p), _p(q), p.shape[0], _p(out), _p(ok)))
+        return out, bool(ok[0])
+
+    def pairing(self, p, q):
+        p, q = self._pairs(p, q)
+        out = np.zeros((p.shape[0], W_FQ12), dtype=np.uint64)
+        self._check(self._lib.bls_mgpu_pairing_batch(self._m, _p(p), _p(q), _p(out), p.shape[0]))
+        return out
+
+    def _wnaf(self, fn, w, bases, k):
+        bases, k = _arr(bases, w, "bases"), _arr(k, W_FR, "k")
+        if bases.shape[0] != k.shape[0]:
+            raise ValueError("bases and k must have the same length")
+        out = np.zeros_like(bases)
+        self._check(fn(self._m, _p(bases), _p(k), _p(out), bases.shape[0]))
+        return out
+
+    def g1_wnaf_mul(self, bases, k):
+        return self._wnaf(self._lib.bls_mgpu_g1_wnaf_mul_batch, W_G1, bases, k)
+
+    def g2_wnaf_mul(self, bases, k):
+        return self._wnaf(self._lib.bls_mgpu_g2_wnaf_mul_batch, W_G2, bases, k)
+
+    def last_phase_ms(self):
+        ms = (ctypes.c_double * 3)()
+        self._check(self._lib.bls_mgpu_last_phase_ms(self._m, ms))
+        return {"shards_ms": ms[0], "tail_ms": ms[1], "total_ms": ms[2]}

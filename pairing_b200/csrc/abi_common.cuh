@@ -62,8 +62,17 @@ struct bls_ctx {
   int sm_count;
   cudaStream_t stream;
   uint64_t launches;
+  size_t wide_pairing_max, wide_final_exp_max;   // batches up to these sizes run on the warp-cooperative engine (kernels_wide.cu)
   char last_error[256];
 };
+// Defaults of the two limits: below them one WARP per element (~2 ms for one pairing or for a thousand) beats the lane-pair
+// throughput kernels (9.9 ms of latency, 1.37 M pairings/s); bls_ctx_set_latency_path_limits overrides them per context.
+#ifndef BLS_WIDE_PAIRING_MAX
+#define BLS_WIDE_PAIRING_MAX 4096
+#endif
+#ifndef BLS_WIDE_FINAL_EXP_MAX
+#define BLS_WIDE_FINAL_EXP_MAX 4096
+#endif
 
 #define CK(call)                                                                      \
   do {                                                                                \
@@ -104,10 +113,40 @@ static inline cudaStream_t pick(bls_ctx* ctx, void* stream) { return stream ? (c
     CK(cudaGetLastError());                             \
   } while (0)
 
+// ---- host-buffer entry points stage through stream-ordered device buffers
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  cudaStream_t s;
+  explicit DevBuf(cudaStream_t s_) : s(s_) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
+  ~DevBuf() { if (p) cudaFreeAsync(p, s); }
+};
+}  // namespace
+
+#define H2D(buf, host, bytes)                                                          \
+  DevBuf buf(ctx->stream);                                                             \
+  CK(buf.alloc(bytes));                                                                \
+  if (host) CK(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream))
+#define DALLOC(buf, bytes) \
+  DevBuf buf(ctx->stream); \
+  CK(buf.alloc(bytes))
+#define D2H(host, buf, bytes) CK(cudaMemcpyAsync(host, buf.p, bytes, cudaMemcpyDeviceToHost, ctx->stream))
+#define SYNC() CK(cudaStreamSynchronize(ctx->stream))
+#define TRY(call)            \
+  do {                       \
+    int rc_ = (call);        \
+    if (rc_ != BLS_OK) return rc_; \
+  } while (0)
+
+
 #define BLS_INTERNAL __attribute__((visibility("hidden")))
 // cross-unit helpers (not part of the ABI)
 extern "C" {
 BLS_INTERNAL int bls_internal_product_passes(bls_ctx* ctx, const uint64_t* in, size_t count, bls_fq12* out1, uint64_t* scratch, cudaStream_t s);
 BLS_INTERNAL size_t bls_internal_mm_lane_pairs(const bls_ctx* ctx, size_t n);
+BLS_INTERNAL int bls_internal_wide_final_exp(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n, cudaStream_t s);
+BLS_INTERNAL int bls_internal_wide_pairing(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, cudaStream_t s);
+BLS_INTERNAL int bls_internal_product_tail(bls_ctx* ctx, const bls_fq12* in, size_t count, bls_fq12* out1, int final_exp, uint8_t* is_some, cudaStream_t s);
 BLS_INTERNAL int bls_internal_multi_miller_prepared(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* qp, size_t n, bls_fq12* partials, cudaStream_t s);
 }

@@ -575,6 +575,8 @@ bls_ctx* bls_ctx_create(int device, int* err) {
   if (!ctx) { if (err) *err = BLS_ERR_OUT_OF_MEMORY; return nullptr; }
   ctx->device = device;
   ctx->launches = 0;
+  ctx->wide_pairing_max = BLS_WIDE_PAIRING_MAX;
+  ctx->wide_final_exp_max = BLS_WIDE_FINAL_EXP_MAX;
   ctx->last_error[0] = 0;
   DevGuard guard;
   if (guard.enter(device) != cudaSuccess ||
@@ -612,6 +614,12 @@ const char* bls_ctx_last_error(const bls_ctx* ctx) { return ctx ? ctx->last_erro
 int bls_ctx_device(const bls_ctx* ctx) { return ctx ? ctx->device : -1; }
 int bls_ctx_sm_count(const bls_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t bls_ctx_launch_count(const bls_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int bls_ctx_set_latency_path_limits(bls_ctx* ctx, size_t max_pairings, size_t max_final_exps) {
+  if (!ctx) return BLS_ERR_INVALID_ARGUMENT;
+  ctx->wide_pairing_max = max_pairings;
+  ctx->wide_final_exp_max = max_final_exps;
+  return BLS_OK;
+}
 
 }  // extern "C"
 
@@ -736,32 +744,7 @@ int bls_g2_batch_normalization_dev(bls_ctx* ctx, bls_g2* inout, size_t n, void* 
 
 }  // extern "C"
 
-// ---- host-pointer entry points: stage through stream-ordered device buffers -----------------------
-namespace {
-struct DevBuf {
-  void* p = nullptr;
-  cudaStream_t s;
-  explicit DevBuf(cudaStream_t s_) : s(s_) {}
-  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
-  ~DevBuf() { if (p) cudaFreeAsync(p, s); }
-};
-}  // namespace
-
-#define H2D(buf, host, bytes)                                                          \
-  DevBuf buf(ctx->stream);                                                             \
-  CK(buf.alloc(bytes));                                                                \
-  if (host) CK(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream))
-#define DALLOC(buf, bytes) \
-  DevBuf buf(ctx->stream); \
-  CK(buf.alloc(bytes))
-#define D2H(host, buf, bytes) CK(cudaMemcpyAsync(host, buf.p, bytes, cudaMemcpyDeviceToHost, ctx->stream))
-#define SYNC() CK(cudaStreamSynchronize(ctx->stream))
-#define TRY(call)            \
-  do {                       \
-    int rc_ = (call);        \
-    if (rc_ != BLS_OK) return rc_; \
-  } while (0)
-
+// ---- host-pointer entry points: stage through stream-ordered device buffers (DevBuf, H2D/D2H: abi_common.cuh)
 extern "C" {
 
 int bls_g2_prepare_batch(bls_ctx* ctx, const bls_g2_affine* q, bls_g2_prepared* out, size_t n) {
@@ -820,30 +803,35 @@ static int shared_q_host(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prep
 int bls_miller_loop_shared_q_batch(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q1, bls_fq12* out, size_t n) { return shared_q_host(ctx, p, q1, out, n, 0); }
 int bls_pairing_shared_q_batch(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q1, bls_fq12* out, size_t n) { return shared_q_host(ctx, p, q1, out, n, 1); }
 
-int bls_multi_miller_loop(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1) {
+static int multi_miller_host(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, int final_exp, uint8_t* is_some) {
   if (!ctx || !out1 || (n && (!p || !q))) return BLS_ERR_INVALID_ARGUMENT;
   USE_DEVICE(ctx);
   H2D(dp, p, n * sizeof(*p));
   H2D(dq, q, n * sizeof(*q));
   DALLOC(dscr, bls_multi_miller_scratch_bytes(ctx, n));
-  DALLOC(dout, sizeof(*out1));
-  TRY(bls_multi_miller_loop_dev(ctx, (const bls_g1_affine*)dp.p, (const bls_g2_affine*)dq.p, n, (bls_fq12*)dout.p, dscr.p, nullptr));
+  DALLOC(dout, sizeof(*out1) + 8);
+  uint8_t* dsome = (uint8_t*)dout.p + sizeof(*out1);
+  if (final_exp) TRY(bls_pairing_product_dev(ctx, (const bls_g1_affine*)dp.p, (const bls_g2_affine*)dq.p, n, (bls_fq12*)dout.p, dsome, dscr.p, nullptr));
+  else TRY(bls_multi_miller_loop_dev(ctx, (const bls_g1_affine*)dp.p, (const bls_g2_affine*)dq.p, n, (bls_fq12*)dout.p, dscr.p, nullptr));
   D2H(out1, dout, sizeof(*out1));
+  if (final_exp && is_some) CK(cudaMemcpyAsync(is_some, dsome, 1, cudaMemcpyDeviceToHost, ctx->stream));
   SYNC();
   return BLS_OK;
 }
+int bls_multi_miller_loop(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1) { return multi_miller_host(ctx, p, q, n, out1, 0, nullptr); }
+// final_exponentiation(miller_loop(pairs)) in one call -- the batch-verification shape of BASELINE configs[2]
+int bls_pairing_product(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, uint8_t* is_some) { return multi_miller_host(ctx, p, q, n, out1, 1, is_some); }
 
 int bls_multi_miller_loop_prepared(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* q, size_t n, bls_fq12* out1) {
   if (!ctx || !out1 || (n && (!p || !q))) return BLS_ERR_INVALID_ARGUMENT;
   USE_DEVICE(ctx);
   H2D(dp, p, n * sizeof(*p));
   H2D(dq, q, n * sizeof(*q));
-  size_t T = bls_internal_mm_lane_pairs(ctx, n);
+  size_t T = bls_internal_mm_lane_pairs(ctx, n);      // one partial product per block
   DALLOC(dpart, T * sizeof(bls_fq12));
-  DALLOC(dscr, bls_fq12_product_scratch_bytes(ctx, T));
   DALLOC(dout, sizeof(*out1));
-  TRY(bls_internal_multi_miller_prepared(ctx, (const bls_g1_affine*)dp.p, (const bls_g2_prepared*)dq.p, n, (bls_fq12*)dpart.p, ctx->stream));
-  TRY(bls_internal_product_passes(ctx, (const uint64_t*)dpart.p, T, (bls_fq12*)dout.p, (uint64_t*)dscr.p, ctx->stream));
+  if (n) TRY(bls_internal_multi_miller_prepared(ctx, (const bls_g1_affine*)dp.p, (const bls_g2_prepared*)dq.p, n, (bls_fq12*)dpart.p, ctx->stream));
+  TRY(bls_internal_product_tail(ctx, (const bls_fq12*)dpart.p, n ? T : 0, (bls_fq12*)dout.p, 0, nullptr, ctx->stream));
   D2H(out1, dout, sizeof(*out1));
   SYNC();
   return BLS_OK;
@@ -1131,6 +1119,37 @@ int bls_field_op_batch(bls_ctx* ctx, int degree, int op, const void* a, const vo
     case 12: k_fq12_op<<<g, TPB, 0, ctx->stream>>>(op, (const uint64_t*)da.p, pb, (uint64_t*)dout.p, (uint8_t*)dok.p, n); break;
   }
   LAUNCH_CHECK();
+  D2H(out, dout, n * eb);
+  if (ok) D2H(ok, dok, n);
+  SYNC();
+  return BLS_OK;
+}
+
+int bls_pair_field_op_batch(bls_ctx* ctx, int degree, int op, const void* a, const void* b, void* out, uint8_t* ok, size_t n) {
+  if (!ctx || (degree != 2 && degree != 6 && degree != 12) || (n && (!a || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  bool valid = false, binary = false;
+  switch (op) {
+    case BLS_OP_ADD: case BLS_OP_SUB: valid = degree != 12; binary = true; break;
+    case BLS_OP_MUL: valid = true; binary = true; break;
+    case BLS_OP_SQR: case BLS_OP_INV: valid = true; break;
+    case BLS_OP_NEG: valid = degree != 12; break;
+    case BLS_OP_DBL: valid = degree == 2; break;
+    case BLS_OP_MUL_NONRES: valid = degree != 12; break;
+    case BLS_OP_FROB1: valid = true; break;
+    case BLS_OP_FROB2: case BLS_OP_FROB3: valid = degree >= 6; break;
+    case BLS_OP_CONJ: case BLS_OP_CYCLOTOMIC_SQR: valid = degree == 12; break;
+    case BLS_OP_MUL_BY_014: case BLS_OP_MUL_BY_LINE_PAIR: valid = degree == 12; binary = true; break;
+    case BLS_OP_MUL_BY_01: case BLS_OP_MUL_BY_1: valid = degree == 6; binary = true; break;
+  }
+  if (!valid || (binary && n && !b)) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  USE_DEVICE(ctx);
+  size_t eb = (size_t)degree * sizeof(bls_fq);
+  H2D(da, a, n * eb);
+  H2D(db, binary ? b : nullptr, binary ? n * eb : 1);
+  DALLOC(dout, n * eb);
+  DALLOC(dok, n);
+  TRY(bls_pair_field_op_dev(ctx, degree, op, da.p, binary ? db.p : nullptr, dout.p, (uint8_t*)dok.p, n, nullptr));
   D2H(out, dout, n * eb);
   if (ok) D2H(ok, dok, n);
   SYNC();

@@ -206,6 +206,36 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller_sha
   }
 }
 
+// One partial product per BLOCK: the 64 lane pairs of a block fold their accumulators by a shared-memory tree (6 levels of
+// Fq12 products) and lane pair 0 stores the result -- 296 partials per launch instead of 18 944, so that ONE small tail
+// kernel (kernels_wide.cu: k_pair_product_tail) finishes the product.  Whole warps only: below 16 lane pairs the other lane
+// pairs of warp 0 multiply along (every lane of a warp has to reach the shuffles inside p2_mul); their results are unused.
+#define MM_LP (BLS_PAIR_TPB / 2)
+__device__ __forceinline__ void mm_block_reduce_store(P12& f, uint64_t* partial) {
+  __shared__ uint32_t s_tree[(MM_LP / 2) * 144];       // at level s the lane pairs [s, 2s) publish, the lane pairs [0, s) multiply
+  const int lp = threadIdx.x >> 1;
+#pragma unroll 1
+  for (int s = MM_LP / 2; s >= 1; s >>= 1) {
+    __syncthreads();
+    if (lp >= s && lp < 2 * s) {
+      uint32_t* dst = s_tree + (lp - s) * 144 + pair_c() * 72;
+      const uint32_t* w = reinterpret_cast<const uint32_t*>(&f);
+#pragma unroll
+      for (int k = 0; k < 72; k++) dst[k] = w[k];
+    }
+    __syncthreads();
+    if (lp < (s < 16 ? 16 : s)) {
+      P12 x;
+      const uint32_t* src = s_tree + lp * 144 + pair_c() * 72;
+      uint32_t* w = reinterpret_cast<uint32_t*>(&x);
+#pragma unroll
+      for (int k = 0; k < 72; k++) w[k] = src[k];
+      p12_mul(f, f, x);
+    }
+  }
+  if (lp == 0) st_p12(partial, f);
+}
+
 // ONE miller_loop over n prepared pairs: lane pair t owns pairs t, t+T, ... and one accumulator (see k_pair_multi_miller)
 __device__ __forceinline__ PLine mm_prepared_line(const uint64_t* p, const uint64_t* qp, size_t n, size_t i, int idx) {
   const bool in_range = i < n;
@@ -241,7 +271,7 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_MM_MINB) k_pair_multi_miller
     if (b >= 0) p12_sqr(f, f);
   }
   p12_conjugate(f);
-  st_p12(partials + FQ12_W * t, f);
+  mm_block_reduce_store(f, partials + FQ12_W * blockIdx.x);
 }
 
 __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_final_exp(const uint64_t* in, uint64_t* out, uint8_t* is_some, size_t n) {
@@ -359,11 +389,89 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_MM_MINB) k_pair_multi_miller
     if (b >= 0) p12_sqr(f, f);
   }
   p12_conjugate(f);
-  st_p12(partials + FQ12_W * t, f);
+  mm_block_reduce_store(f, partials + FQ12_W * blockIdx.x);
+}
+
+// Field-tower operations ON LANE PAIRS (pair_tower.cuh -- the code the pairing kernels run), element-wise, for parity
+// tests on edge operands: the thread-per-element tower behind bls_field_op_batch is a different implementation.
+// Operands may be any representative in [0, 2q] (the relaxed range of fp.cuh); results are stored canonical.
+__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_field_op(int degree, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, uint8_t* ok, size_t n) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t i = t >> 1;
+  const bool active = i < n;
+  if (!active) i = n - 1;
+  bool good = true;
+  if (degree == 2) {
+    const P2 x = ld_p2(a + 12 * i), y = b ? ld_p2(b + 12 * i) : p2_zero();
+    P2 r = p2_zero();
+    switch (op) {
+      case BLS_OP_ADD: r = p2_add(x, y); break;
+      case BLS_OP_SUB: r = p2_sub(x, y); break;
+      case BLS_OP_MUL: r = p2_mul(x, y); break;
+      case BLS_OP_SQR: r = p2_sqr(x); break;
+      case BLS_OP_NEG: r = p2_neg(x); break;
+      case BLS_OP_DBL: r = p2_dbl(x); break;
+      case BLS_OP_INV: good = p2_inv(r, x); if (!good) r = p2_zero(); break;
+      case BLS_OP_MUL_NONRES: r = p2_mul_by_nonresidue(x); break;
+      case BLS_OP_FROB1: r = p2_frobenius(x, 1); break;
+    }
+    if (active) st_p2(out + 12 * i, r);
+  } else if (degree == 6) {
+    P6 x, y, r;
+    x.c0 = ld_p2(a + 36 * i); x.c1 = ld_p2(a + 36 * i + 12); x.c2 = ld_p2(a + 36 * i + 24);
+    if (b) { y.c0 = ld_p2(b + 36 * i); y.c1 = ld_p2(b + 36 * i + 12); y.c2 = ld_p2(b + 36 * i + 24); } else p6_zero(y);
+    p6_zero(r);
+    switch (op) {
+      case BLS_OP_ADD: p6_add(r, x, y); break;
+      case BLS_OP_SUB: p6_sub(r, x, y); break;
+      case BLS_OP_MUL: p6_mul(r, x, y); break;
+      case BLS_OP_SQR: p6_sqr(r, x); break;
+      case BLS_OP_NEG: p6_neg(r, x); break;
+      case BLS_OP_INV: good = p6_inv(r, x); if (!good) p6_zero(r); break;
+      case BLS_OP_MUL_NONRES: p6_mul_by_nonresidue(r, x); break;
+      case BLS_OP_FROB1: p6_frobenius(r, x, 1); break;
+      case BLS_OP_FROB2: p6_frobenius(r, x, 2); break;
+      case BLS_OP_FROB3: p6_frobenius(r, x, 3); break;
+      case BLS_OP_MUL_BY_01: p6_mul_by_01(r, x, y.c0, y.c1); break;
+      case BLS_OP_MUL_BY_1: p6_mul_by_1(r, x, y.c1); break;
+    }
+    if (active) { st_p2(out + 36 * i, r.c0); st_p2(out + 36 * i + 12, r.c1); st_p2(out + 36 * i + 24, r.c2); }
+  } else {
+    P12 x, y, r;
+    ld_p12(x, a + FQ12_W * i);
+    if (b) ld_p12(y, b + FQ12_W * i); else p12_one(y);
+    p6_zero(r.c0); p6_zero(r.c1);
+    switch (op) {
+      case BLS_OP_MUL: p12_mul(r, x, y); break;
+      case BLS_OP_SQR: p12_sqr(r, x); break;
+      case BLS_OP_CYCLOTOMIC_SQR: p12_cyclotomic_sqr(r, x); break;
+      case BLS_OP_INV: good = p12_inv(r, x); if (!good) { p6_zero(r.c0); p6_zero(r.c1); } break;
+      case BLS_OP_CONJ: r = x; p12_conjugate(r); break;
+      case BLS_OP_FROB1: p12_frobenius(r, x, 1); break;
+      case BLS_OP_FROB2: p12_frobenius(r, x, 2); break;
+      case BLS_OP_FROB3: p12_frobenius(r, x, 3); break;
+      case BLS_OP_MUL_BY_014: r = x; p12_mul_by_014(r, y.c0.c0, y.c0.c1, y.c1.c1); break;
+      case BLS_OP_MUL_BY_LINE_PAIR: {      // b packs two lines: (l.c0, l.c1, l.c4, m.c0, m.c1, m.c4)
+        r = x;
+        p12_mul_by_line_pair(r, PLine{y.c0.c0, y.c0.c1, y.c0.c2}, PLine{y.c1.c0, y.c1.c1, y.c1.c2});
+        break;
+      }
+    }
+    if (active) st_p12(out + FQ12_W * i, r);
+  }
+  if (active && ok && pair_c() == 0) ok[i] = good;
 }
 
 extern "C" {
 
+int bls_pair_field_op_dev(bls_ctx* ctx, int degree, int op, const void* a, const void* b, void* out, uint8_t* ok, size_t n, void* stream) {
+  if (!ctx || (degree != 2 && degree != 6 && degree != 12) || (n && (!a || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  USE_DEVICE(ctx);
+  k_pair_field_op<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>(degree, op, (const uint64_t*)a, (const uint64_t*)b, (uint64_t*)out, ok, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
 
 int bls_g2_prepare_dev(bls_ctx* ctx, const bls_g2_affine* q, bls_g2_prepared* out, size_t n, void* stream) {
   if (!ctx || (n && (!q || !out))) return BLS_ERR_INVALID_ARGUMENT;
@@ -394,6 +502,7 @@ int bls_final_exponentiation_dev(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out
   if (!ctx || (n && (!in || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   USE_DEVICE(ctx);
+  if (n <= ctx->wide_final_exp_max) return bls_internal_wide_final_exp(ctx, in, out, is_some, n, pick(ctx, stream));
   k_pair_final_exp<<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, 0, pick(ctx, stream)>>>((const uint64_t*)in, (uint64_t*)out, is_some, n);
   LAUNCH_CHECK();
   return BLS_OK;
@@ -402,6 +511,7 @@ int bls_pairing_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q
   if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   USE_DEVICE(ctx);
+  if (n <= ctx->wide_pairing_max) return bls_internal_wide_pairing(ctx, p, q, out, n, pick(ctx, stream));
   CK(pair_miller_smem_optin<true>());
   k_pair_miller<true><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, pair_miller_smem_bytes(), pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();
@@ -437,31 +547,41 @@ static size_t mm_threads(const bls_ctx* ctx, size_t n) {
 size_t bls_multi_miller_scratch_bytes(const bls_ctx* ctx, size_t n) {
   if (!ctx) return 0;
   size_t T = mm_threads(ctx, n);
-  return mm_rstate_words(n) * sizeof(uint32_t) + T * sizeof(bls_fq12) + bls_fq12_product_scratch_bytes(ctx, T);
+  return mm_rstate_words(n) * sizeof(uint32_t) + (T / MM_LP) * sizeof(bls_fq12);
 }
 
-int bls_multi_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, void* scratch, void* stream) {
+// mod.rs:40-102 over ONE n-pair call: the Miller kernel leaves one partial product per block, the tail kernel folds them
+// (and, for bls_pairing_product_dev, runs the single final exponentiation on the warp-cooperative engine)
+static int multi_miller_impl(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, void* scratch, void* stream, int final_exp, uint8_t* is_some) {
   if (!ctx || !out1 || (n && (!p || !q || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
   USE_DEVICE(ctx);
   cudaStream_t s = pick(ctx, stream);
-  if (n == 0) {
-    return bls_fq12_product_dev(ctx, nullptr, 0, out1, nullptr, stream);   // the empty product: one
-  }
+  if (n == 0) return bls_internal_product_tail(ctx, nullptr, 0, out1, final_exp, is_some, s);   // the empty product: one
   size_t T = mm_threads(ctx, n);
   uint32_t* rstate = (uint32_t*)scratch;
   uint64_t* partials = (uint64_t*)((char*)scratch + mm_rstate_words(n) * sizeof(uint32_t));
-  uint64_t* prod_scratch = partials + T * FQ12_W;
-  k_pair_multi_miller<<<(unsigned)(2 * T / BLS_PAIR_TPB), BLS_PAIR_TPB, 0, s>>>((const uint64_t*)p, (const uint64_t*)q, n, rstate, partials);
+  k_pair_multi_miller<<<(unsigned)(T / MM_LP), BLS_PAIR_TPB, 0, s>>>((const uint64_t*)p, (const uint64_t*)q, n, rstate, partials);
   LAUNCH_CHECK();
-  return bls_internal_product_passes(ctx, partials, T, out1, prod_scratch, s);
+  return bls_internal_product_tail(ctx, (const bls_fq12*)partials, T / MM_LP, out1, final_exp, is_some, s);
+}
+int bls_multi_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, void* scratch, void* stream) {
+  return multi_miller_impl(ctx, p, q, n, out1, scratch, stream, 0, nullptr);
+}
+int bls_pairing_product_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, uint8_t* is_some, void* scratch, void* stream) {
+  return multi_miller_impl(ctx, p, q, n, out1, scratch, stream, 1, is_some);
+}
+int bls_fq12_product_tail_dev(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq12* out1, int final_exp, uint8_t* is_some, void* stream) {
+  if (!ctx || !out1 || (n && !in)) return BLS_ERR_INVALID_ARGUMENT;
+  USE_DEVICE(ctx);
+  return bls_internal_product_tail(ctx, in, n, out1, final_exp, is_some, pick(ctx, stream));
 }
 
 }  // extern "C"
 
-size_t bls_internal_mm_lane_pairs(const bls_ctx* ctx, size_t n) { return mm_threads(ctx, n); }
+size_t bls_internal_mm_lane_pairs(const bls_ctx* ctx, size_t n) { return mm_threads(ctx, n) / MM_LP; }   // = partial products (one per block)
 int bls_internal_multi_miller_prepared(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* qp, size_t n, bls_fq12* partials, cudaStream_t s) {
   const size_t T = mm_threads(ctx, n);
-  k_pair_multi_miller_prepared<<<(unsigned)(2 * T / BLS_PAIR_TPB), BLS_PAIR_TPB, 0, s>>>((const uint64_t*)p, (const uint64_t*)qp, n, (uint64_t*)partials);
+  k_pair_multi_miller_prepared<<<(unsigned)(T / MM_LP), BLS_PAIR_TPB, 0, s>>>((const uint64_t*)p, (const uint64_t*)qp, n, (uint64_t*)partials);
   LAUNCH_CHECK();
   return BLS_OK;
 }

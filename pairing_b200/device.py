@@ -97,6 +97,27 @@ class DeviceEngine:
         self.ctx.call_dev("bls_multi_miller_loop_dev", p.data_ptr(), q.data_ptr(), n, out.data_ptr(), scr.data_ptr(), self._stream())
         return out
 
+    def pairing_product(self, p, q, out=None):
+        """final_exponentiation(miller_loop(all pairs of this device)) -> ((1, 72), is_some (1,) uint8)."""
+        _check(p, nat.W_G1A, "p"); _check(q, nat.W_G2A, "q")
+        n = p.shape[0]
+        if out is None:
+            out = torch.empty((1, nat.W_FQ12), dtype=torch.int64, device=self.device)
+        ok = torch.empty(1, dtype=torch.uint8, device=self.device)
+        scr = self._buf("mm", self.ctx.multi_miller_scratch_bytes(n))
+        self.ctx.call_dev("bls_pairing_product_dev", p.data_ptr(), q.data_ptr(), n, out.data_ptr(), ok.data_ptr(), scr.data_ptr(), self._stream())
+        return out, ok
+
+    def fq12_product_tail(self, f, final_exp=False, out=None):
+        """Product of a few Fq12 values (per-device partials) by one block, optionally followed by the single final
+        exponentiation on the warp-cooperative engine -> ((1, 72), is_some)."""
+        _check(f, nat.W_FQ12, "f")
+        if out is None:
+            out = torch.empty((1, nat.W_FQ12), dtype=torch.int64, device=self.device)
+        ok = torch.ones(1, dtype=torch.uint8, device=self.device)
+        self.ctx.call_dev("bls_fq12_product_tail_dev", f.data_ptr(), f.shape[0], out.data_ptr(), 1 if final_exp else 0, ok.data_ptr(), self._stream())
+        return out, ok
+
     def fq12_pow(self, a, k, out=None):
         _check(a, nat.W_FQ12, "a"); _check(k, nat.W_FR, "k")
         if out is None:

@@ -26,6 +26,17 @@ def all_gather_partials(partial, group=None):
     return out
 
 
+def pairing_product_sharded(eng, p_shard, q_shard, group=None):
+    """final_exponentiation(miller_loop(ALL pairs of all ranks)), BASELINE configs[2] in its stated (strong-scaling) form.
+    eng: DeviceEngine.  Per rank: k_pair_multi_miller + k_pair_product_tail -> one 576-byte partial; all-gather; then the
+    tail kernel once more over the `world` partials with the single final exponentiation (every rank computes it: it is one
+    warp's work and saves a broadcast).  -> ((1, 72), is_some)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return eng.pairing_product(p_shard, q_shard)
+    part = eng.multi_miller_loop(p_shard, q_shard)
+    return eng.fq12_product_tail(all_gather_partials(part, group), final_exp=True)
+
+
 def multi_miller_loop_sharded(local_product, merge, p_shard, q_shard, group=None):
     """local_product(p, q) -> (1,72) partial of this rank's shard; merge(partials (world,72)) -> (1,72).
     With a DeviceEngine: local_product = eng.multi_miller_loop, merge = eng.fq12_product."""

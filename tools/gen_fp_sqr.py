@@ -23,12 +23,16 @@ import random
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import bls_model as m  # noqa: E402
+
+
+class m:   # the base-field modulus (bls12_381/fq.rs:6-13) -- a public constant, no oracle import in build tooling
+    Q = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+
 
 M32 = (1 << 32) - 1
 Q = [(m.Q >> (32 * i)) & M32 for i in range(12)]
-NINV = m.INV32
+NINV = (-pow(m.Q, -1, 1 << 32)) & M32
+assert NINV == 0xfffcfffd
 OUT = os.path.join(ROOT, "pairing_b200", "csrc", "fp_sqr_gen.cuh")
 
 
