@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--prep-log2", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mgpu", action="store_true")
+    ap.add_argument("--no-wnaf-e2e", action="store_true")
     return ap.parse_args()
 
 
@@ -111,7 +112,7 @@ def cpu_secondary_baselines(threads, budget_s=3.0):
     def g2(n):
         reps = (n + 127) // 128
         r = o.g2_op("wnaf", np.tile(b2, (reps, 1))[:n], k=np.tile(k[:128], (reps, 1))[:n], threads=threads)
-        o.g2_batch_normalization(r)
+        r = o.g2_batch_normalization(r)
         o.g2_prepare(o.g2_into_affine(r), threads)
     n, dt = sized(g2, threads * 16)
     out["g2_wnaf_mul_prepare"] = {"value": n / dt, "unit": "scalar-muls/s", "cores": threads, "kind": "port",
@@ -417,6 +418,25 @@ def run_ours(args):
         ms_norm, _ = timed(lambda: eng.g1_batch_normalization_(wout))
         secondary["g1_wnaf_mul"] = entry(nw, ms_mul + ms_norm, MAC32_PER_G1_WNAF, unit="scalar-muls/s", ms_wnaf=ms_mul, ms_normalise=ms_norm,
                                          config="configs[3]: 2^%d points x 255-bit scalars per GPU, wNAF w=4 + batch_normalization" % args.wnaf_log2)
+        # the same through the host-buffer C-ABI calls (pinned buffers): chunked H2D / kernel / D2H pipeline + normalisation
+        if not args.no_wnaf_e2e:
+            bh = torch.empty(bases.shape, dtype=torch.int64).pin_memory(); bh.copy_(bases)
+            kh = torch.empty(ks.shape, dtype=torch.int64).pin_memory(); kh.copy_(ks)
+            oh2 = torch.empty(bases.shape, dtype=torch.int64).pin_memory()
+            torch.cuda.synchronize()
+            def wnaf_e2e():
+                rc = ctx._lib.bls_g1_wnaf_mul_batch(ctx._ctx, bh.data_ptr(), kh.data_ptr(), oh2.data_ptr(), nw)
+                rc = rc or ctx._lib.bls_g1_batch_normalization(ctx._ctx, oh2.data_ptr(), nw)
+                if rc != 0:
+                    raise SystemExit("g1 wnaf e2e failed: %d" % rc)
+            wnaf_e2e()
+            barrier()
+            t0 = time.perf_counter(); wnaf_e2e(); dt = max_over_ranks(time.perf_counter() - t0)
+            secondary["g1_wnaf_mul"]["e2e"] = {"value": world * nw / dt, "unit": "scalar-muls/s", "ms": dt * 1e3,
+                                               "h2d_bytes": nw * (144 + 32) + nw * 144, "d2h_bytes": 2 * nw * 144,
+                                               "api": "bls_g1_wnaf_mul_batch + bls_g1_batch_normalization (host buffers, pinned)",
+                                               "matches_device_path": bool(torch.equal(oh2[:: 4099], wout[:: 4099].cpu()))}
+            del bh, kh, oh2
         del bases, ks, wout
         # configs[4]: G2 wNAF scalar multiplication + batch normalisation + G2Prepared precomputation, 2^20 points per GPU
         n2 = 1 << args.g2_log2

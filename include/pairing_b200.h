@@ -64,6 +64,9 @@ int bls_ctx_device(const bls_ctx* ctx);
 int bls_ctx_sm_count(const bls_ctx* ctx);
 /* number of kernel launches issued through this context so far (bench.py's gpu_launches) */
 uint64_t bls_ctx_launch_count(const bls_ctx* ctx);
+/* The host-buffer entry points stage through device buffers from a per-context memory pool that keeps its memory between
+ * calls (no cudaMalloc / cudaFree per call after the first); bls_ctx_trim hands it back, keeping at most keep_bytes. */
+int bls_ctx_trim(bls_ctx*, size_t keep_bytes);
 /* bls_pairing_* / bls_final_exponentiation_* pick between two kernels by batch size: up to these many elements one WARP
  * works on each element (latency path: ~2 ms for one pairing or for a thousand, the crate's bench_pairing_full shape),
  * above them one lane pair does (throughput path: 9.9 ms of latency, 1.37 M pairings/s).  Same bits either way.

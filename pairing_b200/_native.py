@@ -24,7 +24,7 @@ PT_OPS = dict(double=0, add=1, add_mixed=2, negate=3, sub=6)
 # every symbol include/pairing_b200.h declares (tests/test_abi.py checks the header against this list)
 SYMBOLS = [
     "bls_ctx_create", "bls_ctx_destroy", "bls_strerror", "bls_ctx_last_error", "bls_ctx_device",
-    "bls_ctx_sm_count", "bls_ctx_launch_count", "bls_ctx_set_latency_path_limits",
+    "bls_ctx_sm_count", "bls_ctx_launch_count", "bls_ctx_set_latency_path_limits", "bls_ctx_trim",
     "bls_g2_prepare_batch", "bls_miller_loop_batch", "bls_miller_loop_prepared_batch",
     "bls_multi_miller_loop", "bls_multi_miller_loop_prepared", "bls_final_exponentiation_batch",
     "bls_pairing_batch", "bls_fq12_product",
@@ -82,6 +82,7 @@ def load():
     lib.bls_ctx_launch_count.restype = ctypes.c_uint64
     lib.bls_ctx_launch_count.argtypes = [vp]
     lib.bls_ctx_set_latency_path_limits.argtypes = [vp, sz, sz]
+    lib.bls_ctx_trim.argtypes = [vp, sz]
     for name in ("bls_multi_miller_scratch_bytes", "bls_fq12_product_scratch_bytes"):
         getattr(lib, name).restype = sz
         getattr(lib, name).argtypes = [vp, sz]
@@ -224,6 +225,10 @@ class Context:
     @property
     def launch_count(self):
         return int(self._lib.bls_ctx_launch_count(self._ctx))
+
+    def trim(self, keep_bytes=0):
+        """release the staging memory the context caches between host-buffer calls"""
+        self._check(self._lib.bls_ctx_trim(self._ctx, int(keep_bytes)))
 
     def set_latency_path_limits(self, max_pairings, max_final_exps):
         """Batch sizes up to which pairing / final_exponentiation run one WARP per element (0: lane-pair kernels always)."""

@@ -61,6 +61,9 @@ struct bls_ctx {
   int device;
   int sm_count;
   cudaStream_t stream;
+  cudaStream_t copy_in, copy_out;                // the H2D / D2H legs of the chunked host-buffer entry points (run_pipelined)
+  cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
+  cudaMemPool_t pool;                            // staging buffers of the host-buffer entry points: cached across calls
   uint64_t launches;
   size_t wide_pairing_max, wide_final_exp_max;   // batches up to these sizes run on the warp-cooperative engine (kernels_wide.cu)
   char last_error[256];
@@ -118,18 +121,21 @@ namespace {
 struct DevBuf {
   void* p = nullptr;
   cudaStream_t s;
-  explicit DevBuf(cudaStream_t s_) : s(s_) {}
-  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
+  cudaMemPool_t pool;
+  explicit DevBuf(bls_ctx* c) : s(c->stream), pool(c->pool) {}
+  // the context's own pool (release threshold: never), so that a call does not pay cudaMalloc / cudaFree of its staging
+  // buffers again: the first call grows the pool, later calls of the same size find the memory cached
+  cudaError_t alloc(size_t bytes) { return cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, pool, s); }
   ~DevBuf() { if (p) cudaFreeAsync(p, s); }
 };
 }  // namespace
 
 #define H2D(buf, host, bytes)                                                          \
-  DevBuf buf(ctx->stream);                                                             \
+  DevBuf buf(ctx);                                                                     \
   CK(buf.alloc(bytes));                                                                \
   if (host) CK(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream))
 #define DALLOC(buf, bytes) \
-  DevBuf buf(ctx->stream); \
+  DevBuf buf(ctx);         \
   CK(buf.alloc(bytes))
 #define D2H(host, buf, bytes) CK(cudaMemcpyAsync(host, buf.p, bytes, cudaMemcpyDeviceToHost, ctx->stream))
 #define SYNC() CK(cudaStreamSynchronize(ctx->stream))

@@ -22,10 +22,10 @@ struct bls_mgpu {
 
 namespace {
 struct Shard { size_t lo, n; };
-Shard shard_of(size_t n, int parts, int i) {   // contiguous, sizes differ by at most one (pairing_b200/dist.py::shard_range)
-  size_t base = n / parts, rem = n % parts;
-  size_t lo = (size_t)i * base + ((size_t)i < rem ? (size_t)i : rem);
-  return Shard{lo, base + ((size_t)i < rem ? 1 : 0)};
+Shard shard_of(size_t n, int parts, int i) {   // contiguous [n i / parts, n (i + 1) / parts): pairing_b200/dist.py::shard_range
+  const size_t lo = (size_t)((unsigned __int128)n * (unsigned)i / (unsigned)parts);
+  const size_t hi = (size_t)((unsigned __int128)n * (unsigned)(i + 1) / (unsigned)parts);
+  return Shard{lo, hi - lo};
 }
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 

@@ -119,3 +119,56 @@ def test_dedicated_squaring_is_222_wide_macs():
     h = _sass_histogram("k_fpsqr_peak")
     wide = h["IMAD.WIDE.U32"] + h["IMAD.WIDE.U32.X"] + h["IMAD.HI.U32"]
     assert 2 * 222 <= wide <= 2 * 222 + 16, h
+
+
+def _cuobjdump(*args):
+    import shutil
+    import pairing_b200._native as nat
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    return subprocess.check_output([exe] + list(args) + [nat.LIB_PATH], text=True)
+
+
+def _sass_text(name_part):
+    out = _cuobjdump("-sass")
+    keep, on = [], False
+    for line in out.splitlines():
+        if "Function :" in line:
+            on = name_part in line
+        elif on:
+            keep.append(line)
+    return "\n".join(keep)
+
+
+def test_shared_q_kernel_stages_coefficients_with_a_bulk_copy():
+    """k_pair_miller_shared_q loads the 19 584 B of line coefficients by ONE TMA bulk copy completing on an mbarrier:
+    UBLKCP + SYNCS in the SASS"""
+    sass = _sass_text("k_pair_miller_shared_q")
+    assert "UBLKCP" in sass and "SYNCS" in sass
+
+
+def test_resource_usage_of_the_throughput_kernels():
+    """Performance of the headline kernels hangs on ptxas' allocation (abi_common.cuh): pin registers / stack / shared
+    memory so that a perturbing change is caught here, before GPU time is spent (profiles/r2_resource_usage.txt is the
+    committed snapshot).  VERDICT r1 weak 9."""
+    out = _cuobjdump("--dump-resource-usage")
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        if "Function " in line:
+            name = line.split("Function ")[1].rstrip(":").strip()
+        elif "REG:" in line and name:
+            usage[name] = {k: int(v) for k, v in re.findall(r"(REG|STACK|SHARED):(\d+)", line)}
+    def of(part):
+        hits = [v for k, v in usage.items() if part in k]
+        assert hits, part
+        return hits[0]
+    fused = of("k_pair_millerILb1")
+    assert fused["REG"] == 255 and fused["STACK"] <= 4512 and fused["SHARED"] == 0, fused     # 2 blocks x 128 threads per SM
+    mm = of("k_pair_multi_millerPK")
+    assert mm["REG"] == 255 and mm["STACK"] <= 1920 and mm["SHARED"] <= 19456 + 1024, mm
+    g1 = of("k_wnaf_mul_lazykIN3bls2FpELb0ELi3ELi8")
+    assert g1["REG"] <= 96 and g1["STACK"] <= 5488, g1                                          # 5 blocks per SM
+    wide = of("k_wide_pairing")
+    assert wide["REG"] <= 128, wide
