@@ -114,7 +114,8 @@ int bls_fq12_pow_batch(bls_ctx*, const bls_fq12* a, const bls_fr_repr* k, bls_fq
  * to the reference's. */
 int bls_g1_wnaf_mul_batch(bls_ctx*, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n);
 int bls_g2_wnaf_mul_batch(bls_ctx*, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n);
-/* same with an explicit window 2..7 (the crate-internal wnaf_table/wnaf_form/wnaf_exp triple) */
+/* same with an explicit window 2..13 (the crate-internal wnaf_table/wnaf_form/wnaf_exp triple, as swept by
+ * src/tests/curve.rs:78; windows above 7 keep their 2^(w-1)-entry tables in a per-call global-memory scratch) */
 int bls_g1_wnaf_mul_window_batch(bls_ctx*, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n, int window);
 int bls_g2_wnaf_mul_window_batch(bls_ctx*, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n, int window);
 /* Fixed-base mode Wnaf::new().base(g, num_scalars) then .scalar(k_i) for every scalar (wnaf.rs:93-107,

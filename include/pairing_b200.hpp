@@ -66,6 +66,34 @@ class Gpu {
   bls_ctx* ctx_;
 };
 
+// Several devices of one node behind ONE call (bls_mgpu): an n-pair product or batch is split into contiguous shards inside
+// the library; the product's 576-byte partials meet on the first device, which runs the single final exponentiation.
+class MultiGpu {
+ public:
+  explicit MultiGpu(const std::vector<int>& devices) {
+    int err = 0;
+    m_ = bls_mgpu_create(devices.data(), (int)devices.size(), &err);
+    if (!m_) throw Error(err, bls_strerror(err));
+  }
+  ~MultiGpu() { bls_mgpu_destroy(m_); }
+  MultiGpu(const MultiGpu&) = delete;
+  MultiGpu& operator=(const MultiGpu&) = delete;
+  bls_mgpu* handle() const { return m_; }
+  int device_count() const { return bls_mgpu_device_count(m_); }
+  void check(int rc) const {
+    if (rc == BLS_OK) return;
+    std::string msg = bls_strerror(rc);
+    for (int i = 0; i < device_count(); i++) {
+      const char* e = bls_ctx_last_error(bls_mgpu_ctx(m_, i));
+      if (e && *e) msg += std::string(" [device ") + std::to_string(i) + ": " + e + "]";
+    }
+    throw Error(rc, msg);
+  }
+
+ private:
+  bls_mgpu* m_;
+};
+
 inline bool operator==(const Fq12& a, const Fq12& b) { return std::memcmp(&a, &b, sizeof(Fq12)) == 0; }
 inline bool operator!=(const Fq12& a, const Fq12& b) { return !(a == b); }
 
@@ -104,6 +132,32 @@ struct Bls12 {
     if (p.size() != q.size()) throw Error(BLS_ERR_INVALID_ARGUMENT, "miller_loop: length mismatch");
     Fq12 out;
     g.check(bls_multi_miller_loop(g.ctx(), p.data(), q.data(), p.size(), &out));
+    return out;
+  }
+  // the same ONE miller_loop sharded over several devices
+  static Fq12 miller_loop(MultiGpu& g, const std::vector<G1AffinePoint>& p, const std::vector<G2AffinePoint>& q) {
+    if (p.size() != q.size()) throw Error(BLS_ERR_INVALID_ARGUMENT, "miller_loop: length mismatch");
+    Fq12 out;
+    g.check(bls_mgpu_multi_miller_loop(g.handle(), p.data(), q.data(), p.size(), &out));
+    return out;
+  }
+  // final_exponentiation(&miller_loop(pairs)) in one call (the batch-verification shape); nullopt is the reference's None
+  static std::optional<Fq12> pairing_product(Gpu& g, const std::vector<G1AffinePoint>& p, const std::vector<G2AffinePoint>& q) {
+    if (p.size() != q.size()) throw Error(BLS_ERR_INVALID_ARGUMENT, "pairing_product: length mismatch");
+    Fq12 out; uint8_t some = 0;
+    g.check(bls_pairing_product(g.ctx(), p.data(), q.data(), p.size(), &out, &some));
+    return some ? std::optional<Fq12>(out) : std::nullopt;
+  }
+  static std::optional<Fq12> pairing_product(MultiGpu& g, const std::vector<G1AffinePoint>& p, const std::vector<G2AffinePoint>& q) {
+    if (p.size() != q.size()) throw Error(BLS_ERR_INVALID_ARGUMENT, "pairing_product: length mismatch");
+    Fq12 out; uint8_t some = 0;
+    g.check(bls_mgpu_pairing_product(g.handle(), p.data(), q.data(), p.size(), &out, &some));
+    return some ? std::optional<Fq12>(out) : std::nullopt;
+  }
+  static std::vector<Fq12> pairing(MultiGpu& g, const std::vector<G1AffinePoint>& p, const std::vector<G2AffinePoint>& q) {
+    if (p.size() != q.size()) throw Error(BLS_ERR_INVALID_ARGUMENT, "pairing: length mismatch");
+    std::vector<Fq12> out(p.size());
+    g.check(bls_mgpu_pairing_batch(g.handle(), p.data(), q.data(), out.data(), p.size()));
     return out;
   }
   // n independent single-pair Miller loops

@@ -139,7 +139,8 @@ __device__ __forceinline__ int scalar_num_bits(const Scalar& k) {   // fr.rs:213
 __device__ __forceinline__ int g1_window_for_bits(int nb) { return nb >= 130 ? 4 : (nb >= 34 ? 3 : 2); }
 __device__ __forceinline__ int g2_window_for_bits(int nb) { return nb >= 103 ? 4 : (nb >= 37 ? 3 : 2); }
 
-#define BLS_MAX_WNAF_WINDOW 7          /* per-point tables */
+#define BLS_MAX_WNAF_WINDOW 7          /* per-point tables in per-thread local memory */
+#define BLS_MAX_WNAF_EXPLICIT_WINDOW 13 /* per-point tables in a global-memory scratch row (the reference's test sweep, tests/curve.rs:78) */
 #define BLS_MAX_WNAF_FIXED_WINDOW 16   /* shared table: ec.rs:907-921 picks up to 16 (G1) / 15 (G2) */
 #define BLS_MAX_WNAF_TABLE (1 << (BLS_MAX_WNAF_WINDOW - 1))
 

@@ -260,6 +260,42 @@ __global__ void __launch_bounds__(128, IS_G2 ? BLS_WNAF_MINB : BLS_WNAF_MINB_G1)
   }
 }
 
+// Explicit windows 8..13 of wnaf_table / wnaf_exp (the reference's own test sweeps 2..13, src/tests/curve.rs:78): 2^(w-1) entries
+// per point no longer fit per-thread local memory (590 KB per G1 point at w = 13), so every thread builds its table in a
+// global-memory scratch row and walks it with the same decoupled-lane runner (K = 1).
+template <class F>
+__global__ void __launch_bounds__(128, BLS_WNAF_MINB) k_wnaf_mul_bigwindow(const uint64_t* bases, const uint64_t* k, uint64_t* out, size_t n, int window, uint64_t* tables) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int PW = 3 * FW<F>::W;
+  const size_t tsize = (size_t)1 << (window - 1);
+  const bool active = t < n;
+  const size_t i = active ? t : n - 1;
+  uint64_t* mine = tables + t * tsize * PW;             // rows exist for every launched thread
+  Jac<F> res[1];
+  int32_t digits[1][260];
+  WnafState<1> st;
+  Jac<F> b, dbl;
+  ld_jac(b, bases + (size_t)PW * i);
+  dbl = b;
+  pt_double(dbl);
+#pragma unroll 1
+  for (size_t e = 0; e < tsize; e++) {                  // wnaf_table, wnaf.rs:4-15
+    st_jac(mine + e * PW, b);
+    if (e + 1 < tsize) pt_add(b, dbl);
+  }
+  Scalar s = ld_scalar(k + 4 * i);
+  if (!active) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) s.v[w] = 0;
+  }
+  st.i[0] = wnaf_form(digits[0], s, window) - 1;
+  st.found[0] = false; st.doubled[0] = false;
+  pt_set_zero(res[0]);
+  SharedTable<F> tab{mine};
+  pt_wnaf_run_lazy<F, 1>(res, tab, digits, st);
+  if (active) st_jac(out + (size_t)PW * i, res[0]);
+}
+
 // Fixed-base mode, Wnaf::new().base(g, num_scalars) then .scalar(s_i) per scalar (wnaf.rs:93-107, 169-178):
 // ONE window table shared by all scalars, window 2..16 from recommended_wnaf_for_num_scalars.
 // k_wnaf_table builds it: table[i] = (2i+1) g by repeated projective additions of 2g -- a chain of 2^(w-1)
@@ -655,6 +691,32 @@ int bls_ctx_set_latency_path_limits(bls_ctx* ctx, size_t max_pairings, size_t ma
 }  // extern "C"
 
 // ---- device-pointer entry points --------------------------------------------------------------
+template <class F, bool IS_G2, int KSMALL>
+static int wnaf_mul_dev_impl(bls_ctx* ctx, const void* bases, const bls_fr_repr* k, void* out, size_t n, int window, void* stream) {
+  if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_EXPLICIT_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  USE_DEVICE(ctx);
+  cudaStream_t s = pick(ctx, stream);
+  if (window <= 4) {
+    k_wnaf_mul_lazyk<F, IS_G2, KSMALL, 8><<<blocks_for((n + KSMALL - 1) / KSMALL, TPB), TPB, 0, s>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  } else if (window <= BLS_MAX_WNAF_WINDOW) {
+    k_wnaf_mul_lazyk<F, IS_G2, 1, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, s>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
+  } else {
+    // per-point tables in a stream-ordered scratch allocation from the context's pool
+    const unsigned blocks = blocks_for(n, TPB);
+    const size_t rows = (size_t)blocks * TPB, row_bytes = ((size_t)1 << (window - 1)) * (IS_G2 ? sizeof(bls_g2) : sizeof(bls_g1));
+    void* tables = nullptr;
+    CK(cudaMallocFromPoolAsync(&tables, rows * row_bytes, ctx->pool, s));
+    k_wnaf_mul_bigwindow<F><<<blocks, TPB, 0, s>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window, (uint64_t*)tables);
+    cudaError_t le = cudaGetLastError();
+    cudaFreeAsync(tables, s);
+    ctx->launches++;
+    CK(le);
+    return BLS_OK;
+  }
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
 extern "C" {
 // product tree: a pass over `count` factors uses ceil(count/8) threads
 static size_t prod_threads(size_t count) { return count ? (count + 7) / 8 : 1; }
@@ -693,22 +755,10 @@ int bls_fq12_product_dev(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq12* o
 }
 
 int bls_g1_wnaf_mul_dev(bls_ctx* ctx, const bls_g1* bases, const bls_fr_repr* k, bls_g1* out, size_t n, int window, void* stream) {
-  if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
-  if (!n) return BLS_OK;
-  USE_DEVICE(ctx);
-  if (window <= 4) k_wnaf_mul_lazyk<Fp, false, BLS_WNAF_K, 8><<<blocks_for((n + BLS_WNAF_K - 1) / BLS_WNAF_K, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
-  else k_wnaf_mul_lazyk<Fp, false, 1, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
-  LAUNCH_CHECK();
-  return BLS_OK;
+  return wnaf_mul_dev_impl<Fp, false, BLS_WNAF_K>(ctx, bases, k, out, n, window, stream);
 }
 int bls_g2_wnaf_mul_dev(bls_ctx* ctx, const bls_g2* bases, const bls_fr_repr* k, bls_g2* out, size_t n, int window, void* stream) {
-  if (!ctx || (n && (!bases || !k || !out)) || (window != 0 && (window < 2 || window > BLS_MAX_WNAF_WINDOW))) return BLS_ERR_INVALID_ARGUMENT;
-  if (!n) return BLS_OK;
-  USE_DEVICE(ctx);
-  if (window <= 4) k_wnaf_mul_lazyk<Fp2, true, BLS_WNAF_K_G2, 8><<<blocks_for((n + BLS_WNAF_K_G2 - 1) / BLS_WNAF_K_G2, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
-  else k_wnaf_mul_lazyk<Fp2, true, 1, BLS_MAX_WNAF_TABLE><<<blocks_for(n, TPB), TPB, 0, pick(ctx, stream)>>>((const uint64_t*)bases, (const uint64_t*)k, (uint64_t*)out, n, window);
-  LAUNCH_CHECK();
-  return BLS_OK;
+  return wnaf_mul_dev_impl<Fp2, true, BLS_WNAF_K_G2>(ctx, bases, k, out, n, window, stream);
 }
 
 int bls_g1_wnaf_table_dev(bls_ctx* ctx, const bls_g1* base, int window, bls_g1* table, void* stream) {
@@ -968,11 +1018,11 @@ static int wnaf_host(bls_ctx* ctx, int degree, const void* bases, const bls_fr_r
 int bls_g1_wnaf_mul_batch(bls_ctx* ctx, const bls_g1* b, const bls_fr_repr* k, bls_g1* out, size_t n) { return wnaf_host(ctx, 1, b, k, out, n, 0, 0); }
 int bls_g2_wnaf_mul_batch(bls_ctx* ctx, const bls_g2* b, const bls_fr_repr* k, bls_g2* out, size_t n) { return wnaf_host(ctx, 2, b, k, out, n, 0, 0); }
 int bls_g1_wnaf_mul_window_batch(bls_ctx* ctx, const bls_g1* b, const bls_fr_repr* k, bls_g1* out, size_t n, int window) {
-  if (window < 2 || window > BLS_MAX_WNAF_WINDOW) return BLS_ERR_INVALID_ARGUMENT;
+  if (window < 2 || window > BLS_MAX_WNAF_EXPLICIT_WINDOW) return BLS_ERR_INVALID_ARGUMENT;
   return wnaf_host(ctx, 1, b, k, out, n, window, 0);
 }
 int bls_g2_wnaf_mul_window_batch(bls_ctx* ctx, const bls_g2* b, const bls_fr_repr* k, bls_g2* out, size_t n, int window) {
-  if (window < 2 || window > BLS_MAX_WNAF_WINDOW) return BLS_ERR_INVALID_ARGUMENT;
+  if (window < 2 || window > BLS_MAX_WNAF_EXPLICIT_WINDOW) return BLS_ERR_INVALID_ARGUMENT;
   return wnaf_host(ctx, 2, b, k, out, n, window, 0);
 }
 int bls_g1_mul_batch(bls_ctx* ctx, const bls_g1* b, const bls_fr_repr* k, bls_g1* out, size_t n) { return wnaf_host(ctx, 1, b, k, out, n, 0, 1); }

@@ -9,9 +9,10 @@ fn main() {
     let root = PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("..");
     let lib = out.join("libpairing_b200.a");
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
-    // two translation units: the lane-pair pairing engine is compiled on its own (pairing_b200/csrc/abi_common.cuh)
+    // four translation units: the lane-pair pairing engine and the warp-cooperative engine are compiled on their own
+    // (pairing_b200/csrc/abi_common.cuh); mgpu.cu is the host-side multi-device layer
     let mut objs = Vec::new();
-    for unit in &["kernels", "kernels_pair"] {
+    for unit in &["kernels", "kernels_pair", "kernels_wide", "mgpu"] {
         let src = root.join(format!("pairing_b200/csrc/{}.cu", unit));
         let obj = out.join(format!("{}.o", unit));
         let status = Command::new(&nvcc)
@@ -31,7 +32,9 @@ fn main() {
     println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
-    for f in &["kernels.cu", "kernels_pair.cu", "abi_common.cuh", "fr.cuh", "fp.cuh", "tower.cuh", "curve.cuh", "pair_tower.cuh", "codec.cuh", "constants.cuh"] {
+    println!("cargo:rustc-link-lib=dylib=pthread");
+    for f in &["kernels.cu", "kernels_pair.cu", "kernels_wide.cu", "mgpu.cu", "abi_common.cuh", "fr.cuh", "fp.cuh", "fp_sqr_gen.cuh", "tower.cuh", "curve.cuh",
+               "pair_tower.cuh", "wide.cuh", "wide_prog_gen.cuh", "codec.cuh", "constants.cuh"] {
         println!("cargo:rerun-if-changed={}", root.join("pairing_b200/csrc").join(f).display());
     }
     println!("cargo:rerun-if-changed={}", root.join("include/pairing_b200.h").display());

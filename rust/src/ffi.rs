@@ -14,6 +14,8 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] #[derive(Copy, Clone)] pub struct bls_fr_repr { pub l: [u64; 4] }
 #[repr(C)] #[derive(Copy, Clone)] pub struct bls_g2_prepared { pub coeffs: [[bls_fq2; 3]; 68], pub infinity: u64 }
 pub enum bls_ctx {}
+/// several devices of one node behind one call (include/pairing_b200.h, "several GPUs")
+pub enum bls_mgpu {}
 
 pub const BLS_OK: c_int = 0;
 
@@ -30,6 +32,15 @@ extern "C" {
     pub fn bls_pairing_shared_q_batch(ctx: *mut bls_ctx, p: *const bls_g1_affine, q1: *const bls_g2_prepared, out: *mut bls_fq12, n: usize) -> c_int;
     pub fn bls_multi_miller_loop(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_affine, n: usize, out1: *mut bls_fq12) -> c_int;
     pub fn bls_multi_miller_loop_prepared(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_prepared, n: usize, out1: *mut bls_fq12) -> c_int;
+    pub fn bls_pairing_product(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_affine, n: usize, out1: *mut bls_fq12, is_some: *mut u8) -> c_int;
+    pub fn bls_mgpu_create(devices: *const c_int, n_devices: c_int, err: *mut c_int) -> *mut bls_mgpu;
+    pub fn bls_mgpu_destroy(m: *mut bls_mgpu);
+    pub fn bls_mgpu_device_count(m: *const bls_mgpu) -> c_int;
+    pub fn bls_mgpu_multi_miller_loop(m: *mut bls_mgpu, p: *const bls_g1_affine, q: *const bls_g2_affine, n: usize, out1: *mut bls_fq12) -> c_int;
+    pub fn bls_mgpu_pairing_product(m: *mut bls_mgpu, p: *const bls_g1_affine, q: *const bls_g2_affine, n: usize, out1: *mut bls_fq12, is_some: *mut u8) -> c_int;
+    pub fn bls_mgpu_pairing_batch(m: *mut bls_mgpu, p: *const bls_g1_affine, q: *const bls_g2_affine, out: *mut bls_fq12, n: usize) -> c_int;
+    pub fn bls_mgpu_g1_wnaf_mul_batch(m: *mut bls_mgpu, bases: *const bls_g1, k: *const bls_fr_repr, out: *mut bls_g1, n: usize) -> c_int;
+    pub fn bls_mgpu_g2_wnaf_mul_batch(m: *mut bls_mgpu, bases: *const bls_g2, k: *const bls_fr_repr, out: *mut bls_g2, n: usize) -> c_int;
     pub fn bls_final_exponentiation_batch(ctx: *mut bls_ctx, input: *const bls_fq12, out: *mut bls_fq12, is_some: *mut u8, n: usize) -> c_int;
     pub fn bls_pairing_batch(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_affine, out: *mut bls_fq12, n: usize) -> c_int;
     pub fn bls_g1_decode_batch(ctx: *mut bls_ctx, bytes: *const u8, compressed: c_int, checked: c_int, out: *mut bls_g1_affine, status: *mut u8, n: usize) -> c_int;

@@ -1,7 +1,12 @@
 //! Slice-level GPU entry points next to the `pairing` crate's scalar trait methods.
 //!
-//! This file lives INSIDE a fork of the crate (module `bls12_381::gpu`): the point fields are
-//! `pub(crate)` (src/bls12_381/ec.rs:15-17, 33-35), so marshalling needs crate visibility.  The
+//! This file lives INSIDE a fork of the crate, as the module `crate::bls12_381::gpu` (`mod gpu;` in
+//! src/bls12_381/mod.rs, `ffi.rs` next to it as `gpu/ffi.rs`): the point fields are `pub(crate)`
+//! (src/bls12_381/ec.rs:15-17, 33-35), so marshalling needs crate visibility, and the two accessors it
+//! uses on `Fq` / `Fr` -- `mont_limbs()` and `from_mont_limbs()`, raw access to the Montgomery limbs --
+//! are the two-line patch shown in INTEGRATION.md (the upstream fields are private to fq.rs / fr.rs).
+//! Marshalling through the public API instead (`into_repr` / `from_repr`) would cost a Montgomery
+//! conversion per coordinate in each direction.  The
 //! scalar trait methods (`Engine::pairing`, `CurveProjective::mul_assign`, ...) stay as they are;
 //! callers with batches use the functions below.  One `Gpu` = one `bls_ctx`; it is `Send` and is
 //! wrapped in a `Mutex` because calls on a context must be serialised.
@@ -9,8 +14,8 @@
 //! Authored, not compiled here (no Rust toolchain in the build image) -- see INTEGRATION.md.
 pub mod ffi;
 
-use ffi::*;
-use pairing::bls12_381::{Fq12, FrRepr, G1Affine, G2Affine, G1, G2};
+use self::ffi::*;
+use crate::bls12_381::{Fq12, FrRepr, G1Affine, G2Affine, G1, G2};
 use std::sync::Mutex;
 
 #[derive(Debug)]
@@ -49,6 +54,17 @@ impl Gpu {
         let ctx = self.ctx.lock().unwrap();
         check(unsafe { bls_multi_miller_loop(*ctx, pp.as_ptr(), qq.as_ptr(), p.len(), &mut out) }, *ctx)?;
         Ok(marshal::fq12_back(&out))
+    }
+
+    /// `Bls12::final_exponentiation(&Bls12::miller_loop(pairs))` in one call: the batch-verification shape.
+    pub fn pairing_product(&self, p: &[G1Affine], q: &[G2Affine]) -> Result<Option<Fq12>, GpuError> {
+        assert_eq!(p.len(), q.len());
+        let pp: Vec<bls_g1_affine> = p.iter().map(marshal::g1_affine).collect();
+        let qq: Vec<bls_g2_affine> = q.iter().map(marshal::g2_affine).collect();
+        let (mut out, mut some) = (marshal::FQ12_ZERO, 0u8);
+        let ctx = self.ctx.lock().unwrap();
+        check(unsafe { bls_pairing_product(*ctx, pp.as_ptr(), qq.as_ptr(), p.len(), &mut out, &mut some) }, *ctx)?;
+        Ok(if some != 0 { Some(marshal::fq12_back(&out)) } else { None })
     }
 
     /// `Bls12::final_exponentiation` per element; `None` where the input is zero (mod.rs:104-160).
@@ -156,4 +172,83 @@ mod marshal {
     pub fn g1_affine_back(p: &bls_g1_affine) -> G1Affine { G1Affine { x: fq_back(&p.x), y: fq_back(&p.y), infinity: p.infinity != 0 } }
     pub fn g1(p: &G1) -> bls_g1 { bls_g1 { x: fq(&p.x), y: fq(&p.y), z: fq(&p.z) } }
     pub fn g1_back(p: &bls_g1) -> G1 { G1 { x: fq_back(&p.x), y: fq_back(&p.y), z: fq_back(&p.z) } }
+}
+
+
+/// Several GPUs of one node behind one call: `Engine::miller_loop` takes all pairs of a product at once
+/// (src/bls12_381/mod.rs:40-102), so the sharding, the 576-byte exchange and the single final
+/// exponentiation happen inside the library (pairing_b200/csrc/mgpu.cu).
+pub struct MultiGpu { m: Mutex<*mut bls_mgpu> }
+unsafe impl Send for MultiGpu {}
+unsafe impl Sync for MultiGpu {}
+
+impl MultiGpu {
+    pub fn new(devices: &[i32]) -> Result<MultiGpu, GpuError> {
+        let mut err = 0;
+        let m = unsafe { bls_mgpu_create(devices.as_ptr(), devices.len() as i32, &mut err) };
+        if m.is_null() { return Err(GpuError(err, strerror(err))); }
+        Ok(MultiGpu { m: Mutex::new(m) })
+    }
+
+    /// One `miller_loop` over all pairs, sharded over the devices.
+    pub fn multi_miller_loop(&self, p: &[G1Affine], q: &[G2Affine]) -> Result<Fq12, GpuError> {
+        assert_eq!(p.len(), q.len());
+        let pp: Vec<bls_g1_affine> = p.iter().map(marshal::g1_affine).collect();
+        let qq: Vec<bls_g2_affine> = q.iter().map(marshal::g2_affine).collect();
+        let mut out = marshal::FQ12_ZERO;
+        let m = self.m.lock().unwrap();
+        let rc = unsafe { bls_mgpu_multi_miller_loop(*m, pp.as_ptr(), qq.as_ptr(), p.len(), &mut out) };
+        if rc != 0 { return Err(GpuError(rc, strerror(rc))); }
+        Ok(marshal::fq12_back(&out))
+    }
+
+    /// `final_exponentiation(miller_loop(pairs))` over all devices.
+    pub fn pairing_product(&self, p: &[G1Affine], q: &[G2Affine]) -> Result<Option<Fq12>, GpuError> {
+        assert_eq!(p.len(), q.len());
+        let pp: Vec<bls_g1_affine> = p.iter().map(marshal::g1_affine).collect();
+        let qq: Vec<bls_g2_affine> = q.iter().map(marshal::g2_affine).collect();
+        let (mut out, mut some) = (marshal::FQ12_ZERO, 0u8);
+        let m = self.m.lock().unwrap();
+        let rc = unsafe { bls_mgpu_pairing_product(*m, pp.as_ptr(), qq.as_ptr(), p.len(), &mut out, &mut some) };
+        if rc != 0 { return Err(GpuError(rc, strerror(rc))); }
+        Ok(if some != 0 { Some(marshal::fq12_back(&out)) } else { None })
+    }
+
+    /// Independent pairings, sharded over the devices (no exchange step).
+    pub fn pairing_batch(&self, p: &[G1Affine], q: &[G2Affine]) -> Result<Vec<Fq12>, GpuError> {
+        assert_eq!(p.len(), q.len());
+        let pp: Vec<bls_g1_affine> = p.iter().map(marshal::g1_affine).collect();
+        let qq: Vec<bls_g2_affine> = q.iter().map(marshal::g2_affine).collect();
+        let mut out = vec![marshal::FQ12_ZERO; p.len()];
+        let m = self.m.lock().unwrap();
+        let rc = unsafe { bls_mgpu_pairing_batch(*m, pp.as_ptr(), qq.as_ptr(), out.as_mut_ptr(), p.len()) };
+        if rc != 0 { return Err(GpuError(rc, strerror(rc))); }
+        Ok(out.iter().map(marshal::fq12_back).collect())
+    }
+
+    pub fn g1_wnaf_mul_batch(&self, bases: &[G1], k: &[FrRepr]) -> Result<Vec<G1>, GpuError> {
+        assert_eq!(bases.len(), k.len());
+        let bb: Vec<bls_g1> = bases.iter().map(marshal::g1).collect();
+        let kk: Vec<bls_fr_repr> = k.iter().map(|r| bls_fr_repr { l: r.0 }).collect();
+        let mut out = bb.clone();
+        let m = self.m.lock().unwrap();
+        let rc = unsafe { bls_mgpu_g1_wnaf_mul_batch(*m, bb.as_ptr(), kk.as_ptr(), out.as_mut_ptr(), bb.len()) };
+        if rc != 0 { return Err(GpuError(rc, strerror(rc))); }
+        Ok(out.iter().map(marshal::g1_back).collect())
+    }
+
+    pub fn g2_wnaf_mul_batch(&self, bases: &[G2], k: &[FrRepr]) -> Result<Vec<G2>, GpuError> {
+        assert_eq!(bases.len(), k.len());
+        let bb: Vec<bls_g2> = bases.iter().map(marshal::g2).collect();
+        let kk: Vec<bls_fr_repr> = k.iter().map(|r| bls_fr_repr { l: r.0 }).collect();
+        let mut out = bb.clone();
+        let m = self.m.lock().unwrap();
+        let rc = unsafe { bls_mgpu_g2_wnaf_mul_batch(*m, bb.as_ptr(), kk.as_ptr(), out.as_mut_ptr(), bb.len()) };
+        if rc != 0 { return Err(GpuError(rc, strerror(rc))); }
+        Ok(out.iter().map(marshal::g2_back).collect())
+    }
+}
+
+impl Drop for MultiGpu {
+    fn drop(&mut self) { unsafe { bls_mgpu_destroy(*self.m.lock().unwrap()) } }
 }

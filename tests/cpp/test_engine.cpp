@@ -72,6 +72,20 @@ static std::vector<G2Point> rand_g2(size_t n) {
 }
 
 // src/tests/engine.rs:5-47
+// device count without CUDA headers in this host-only program: the runtime is already loaded through libpairing_b200.so
+#include <dlfcn.h>
+static void cudaGetDeviceCount_shim(int* n) {
+  *n = 0;
+  typedef int (*fn_t)(int*);
+  fn_t fn = (fn_t)dlsym(RTLD_DEFAULT, "cudaGetDeviceCount");
+  if (!fn) {
+    void* h = dlopen("libcudart.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libcudart.so.12", RTLD_NOW | RTLD_GLOBAL);
+    if (h) fn = (fn_t)dlsym(h, "cudaGetDeviceCount");
+  }
+  if (fn) fn(n);
+}
+
 static void engine_tests(Gpu& g) {
   const size_t n = 10;
   auto a = G1::into_affine(g, rand_g1(n));
@@ -132,6 +146,18 @@ static void random_miller_loop_tests(Gpu& g) {
   std::vector<G2AffinePoint> allq(ba); allq.insert(allq.end(), da.begin(), da.end());
   std::vector<Fq12> all(p2); all.insert(all.end(), cd.begin(), cd.end());
   CHECK(*Bls12::final_exponentiation(g, Bls12::miller_loop(g, allp, allq)) == Bls12::product(g, all));
+  // final_exponentiation(miller_loop(pairs)) in one call, and the same product with the pairs sharded over every visible
+  // device inside the library (bls_mgpu_*): one GT element, bit-equal
+  CHECK(*Bls12::pairing_product(g, allp, allq) == Bls12::product(g, all));
+  int ndev = 0;
+  cudaGetDeviceCount_shim(&ndev);
+  std::vector<int> devs;
+  for (int i = 0; i < (ndev > 0 ? ndev : 1); i++) devs.push_back(i);
+  MultiGpu mg(devs);
+  CHECK(mg.device_count() == (int)devs.size());
+  CHECK(Bls12::miller_loop(mg, allp, allq) == Bls12::miller_loop(g, allp, allq));
+  CHECK(*Bls12::pairing_product(mg, allp, allq) == Bls12::product(g, all));
+  CHECK(same(Bls12::pairing(mg, allp, allq), all));
 }
 
 // src/tests/engine.rs:93-126

@@ -19,7 +19,7 @@ def _build(out):
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", out,
                            os.path.join(ROOT, "tests", "cpp", "test_engine.cpp"),
                            "-L", libdir, "-lpairing_b200", "-L", odir, "-lbls_oracle",
-                           "-Wl,-rpath," + libdir, "-Wl,-rpath," + odir])
+                           "-Wl,-rpath," + libdir, "-Wl,-rpath," + odir, "-ldl"])
 
 
 def test_cpp_host_mirror_compiles_and_links():

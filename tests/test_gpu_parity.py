@@ -177,7 +177,7 @@ def test_wnaf_mul_heuristic_windows(ctx, g2):
 
 
 @pytest.mark.parametrize("g2", [False, True])
-@pytest.mark.parametrize("w", [2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("w", [2, 3, 4, 5, 6, 7, 8, 10, 13])
 def test_wnaf_mul_explicit_window(ctx, g2, w):
     n = 48
     bases = (dg.g2_points if g2 else dg.g1_points)(n, 26 + w)

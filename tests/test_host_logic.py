@@ -111,6 +111,69 @@ def test_sharded_multi_miller_gloo_world2():
     assert ret[0] == want and ret[1] == want
 
 
+class _OracleEngine:
+    """the three DeviceEngine methods pairing_product_sharded drives, computed by the oracle (there is no GPU here)"""
+
+    def multi_miller_loop(self, p, q):
+        import torch
+        return torch.from_numpy(o.multi_miller_product(np.asarray(p), np.asarray(q), 1).view(np.int64))
+
+    def fq12_product_tail(self, parts, final_exp=False):
+        import torch
+        f = parts.numpy().view(np.uint64)
+        acc = f[:1].copy()
+        for i in range(1, f.shape[0]):
+            acc = o.fq12_op("mul", acc, f[i:i + 1])[0]
+        ok = np.ones(1, dtype=np.uint8)
+        if final_exp:
+            acc, ok = o.final_exponentiation(acc, 1)
+        return torch.from_numpy(acc.view(np.int64)), torch.from_numpy(ok)
+
+    def pairing_product(self, p, q):
+        return self.fq12_product_tail(self.multi_miller_loop(p, q), final_exp=True)
+
+
+def _worker_product(rank, world, port, n, ret):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = dg.g1_affine_points(n, 33, infinity_at=(2,))
+    q = dg.g2_affine_points(n, 34)
+    lo, hi = pdist.shard_range(n, rank, world)
+    gt, ok = pdist.pairing_product_sharded(_OracleEngine(), p[lo:hi], q[lo:hi])
+    ret[rank] = (gt.numpy().view(np.uint64).tobytes(), int(ok[0]))
+    dist.destroy_process_group()
+
+
+def test_sharded_pairing_product_gloo_world2():
+    """BASELINE configs[2] in its stated form on 2 gloo ranks: ONE product sharded over the ranks, 576-byte partials
+    all-gathered, one final exponentiation == final_exponentiation(miller_loop(all pairs)) of the reference"""
+    import torch.multiprocessing as mp
+    n, world = 9, 2
+    port = _free_port()
+    ret = mp.Manager().dict()
+    procs = [mp.get_context("spawn").Process(target=_worker_product, args=(r, world, port, n, ret)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    for p_ in procs:
+        p_.join(180)
+        assert p_.exitcode == 0
+    p = dg.g1_affine_points(n, 33, infinity_at=(2,))
+    q = dg.g2_affine_points(n, 34)
+    want, wok = o.final_exponentiation(o.multi_miller_loop(p, q), 1)
+    assert ret[0] == ret[1] == (want.tobytes(), int(wok[0]))
+
+
+def test_shard_ranges_partition_every_size():
+    """dist.shard_range (and mgpu.cu's shard_of, the same formula): contiguous, exhaustive, sizes within one of each other"""
+    for n in (0, 1, 7, 8, 9, 1000, (1 << 20) + 3):
+        for world in (1, 2, 3, 4, 8):
+            r = [pdist.shard_range(n, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == n and all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [hi - lo for lo, hi in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
 def test_carry_schedule_of_the_montgomery_products_on_the_relaxed_range():
     """tools/emulate_fp.py replays fp_mul / fp_mul2 (pairing_b200/csrc/fp.cuh) word by word on operands in [0, 2q]: the
     result is congruent, stays <= 2q without a conditional subtraction, and every carry the PTX drops is zero."""
@@ -128,7 +191,8 @@ def test_rust_shim_binds_every_host_entry_point():
     hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(root, "include", "pairing_b200.h")).read(), flags=re.S)
     names = sorted(set(re.findall(r"\b(bls_[a-z0-9_]+)\s*\(", hdr)))
     ffi = open(os.path.join(root, "rust", "src", "ffi.rs")).read()
-    skip = ("_dev", "_scratch_bytes", "bls_imad_peak", "bls_ctx_device", "bls_ctx_sm_count", "bls_ctx_launch_count", "bls_field_op_batch")
+    skip = ("_dev", "_scratch_bytes", "bls_imad_peak", "bls_ctx_device", "bls_ctx_sm_count", "bls_ctx_launch_count", "bls_field_op_batch",
+            "bls_pair_field_op_batch", "bls_ctx_set_latency_path_limits", "bls_ctx_trim", "bls_mgpu_ctx", "bls_mgpu_last_phase_ms")
     missing = [n for n in names if not n.endswith(skip[:2]) and n not in skip and ("fn %s(" % n) not in ffi]
     assert not missing, missing
 

@@ -11,6 +11,7 @@ from pairing_b200.device import DeviceEngine
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--mm-log2", type=int, default=20)
+ap.add_argument("--only-mm", action="store_true")
 args = ap.parse_args()
 eng = DeviceEngine(device=0)
 ctx = eng.ctx
@@ -30,7 +31,7 @@ def timeit(fn, reps=5):
 
 out = torch.empty((N, 72), dtype=torch.int64, device=eng.device)
 print("%8s %12s %12s" % ("n", "wide ms", "lane-pair ms"))
-for n in (1, 10, 100, 500, 1000, 2000, 3000, 4096, 6000, 8192, 16384):
+for n in (() if args.only_mm else (1, 10, 100, 500, 1000, 2000, 3000, 4096, 6000, 8192, 16384)):
     p, q = pa[:n].contiguous(), qa[:n].contiguous()
     ctx.set_latency_path_limits(1 << 30, 1 << 30)
     w = timeit(lambda: eng.pairing(p, q, out[:n]))
@@ -40,7 +41,7 @@ for n in (1, 10, 100, 500, 1000, 2000, 3000, 4096, 6000, 8192, 16384):
     assert torch.equal(ref, out[:n]), "paths differ at n=%d" % n
     print("%8d %12.3f %12.3f" % (n, w, l))
 f = eng.miller_loop_batch(pa[:4096].contiguous(), qa[:4096].contiguous())
-for n in (1, 100, 1000, 4096):
+for n in (() if args.only_mm else (1, 100, 1000, 4096)):
     ctx.set_latency_path_limits(1 << 30, 1 << 30)
     w = timeit(lambda: eng.final_exponentiation(f[:n].contiguous()))
     ctx.set_latency_path_limits(0, 0)
