@@ -211,7 +211,7 @@ template <class F> struct SharedTable {
 #endif
 // blocks per SM: 3 for G2 (168 registers; 3.29 M muls/s at 2^20 against 3.19 M with 2 and 2.90 M with 4), BLS_WNAF_MINB_G1 for G1
 #ifndef BLS_WNAF_MINB_G1
-#define BLS_WNAF_MINB_G1 5   /* 96 registers: 9.69 M G1 muls/s at 2^22 against 9.57 M with 4 blocks and 9.40 M with 6 (one run) */
+#define BLS_WNAF_MINB_G1 4   /* 128 registers.  With the dedicated squaring (r2, 2^22 points, one box): 398.8 ms with 4 blocks, 405.1 with 5 (96 registers), 415.2 with 3, 425.7 with 6; K = 2 at 4 blocks 404.4 */
 #endif
 // MAXT = table entries per point: 8 for the windows the per-scalar heuristics pick (2..4, ec.rs:895-905, 1586-1596),
 // 64 (K = 1) for the explicit windows 5..7 of wnaf_table / wnaf_exp

@@ -169,6 +169,6 @@ def test_resource_usage_of_the_throughput_kernels():
     mm = of("k_pair_multi_millerPK")
     assert mm["REG"] == 255 and mm["STACK"] <= 1920 and mm["SHARED"] <= 19456 + 1024, mm
     g1 = of("k_wnaf_mul_lazykIN3bls2FpELb0ELi3ELi8")
-    assert g1["REG"] <= 96 and g1["STACK"] <= 5488, g1                                          # 5 blocks per SM
+    assert g1["REG"] <= 128 and g1["STACK"] <= 5488, g1                                         # 4 blocks per SM
     wide = of("k_wide_pairing")
     assert wide["REG"] <= 128, wide

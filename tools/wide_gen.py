@@ -14,6 +14,7 @@ the canonical outputs are bit-identical.
 
 A round is one of
   MUL  every active lane pair:  dst <- (sum of <= 4 terms) * (sum of <= 4 terms)      (one lazily reduced dual product per lane)
+  MUL4 the same product with FOUR lanes per micro-op (rounds of at most 8 products): one plain product per lane
   LIN  every active lane pair:  dst <- sum of <= 8 terms
   INV  the whole warp:          dst <- src^-1 in Fq2                                  (fq2.rs:138-155)
 and a term is  [-] 2^k [xi] [conj] slot.
@@ -31,7 +32,7 @@ Q = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb1
 BLS_X = 0xd201000000010000            # |x|; x is negative (mod.rs:15-16)
 W = 16                                # lane pairs of a warp
 T_MUL, T_LIN = 4, 8                   # terms per multiplication operand / per linear micro-op
-K_MUL, K_LIN, K_INV = 0, 1, 2
+K_MUL, K_LIN, K_INV, K_MUL4 = 0, 1, 2, 3
 NONE = 0xffff
 COST = {"mul": 1.0, "lin": 0.25, "inv": 240.0, "in": 0.0, "const": 0.0}
 
@@ -560,6 +561,8 @@ def encode(prog):
     code = []
     for kind, ops in prog.rounds:
         k = {"mul": K_MUL, "lin": K_LIN, "inv": K_INV}[kind]
+        if kind == "mul" and len(ops) <= W // 2:
+            k = K_MUL4          # at most 8 products: FOUR lanes per product, one plain Montgomery product each (wide.cuh)
         nt = max([max(len(a), len(b)) for _, a, b in ops], default=0)
         code += [k | (len(ops) << 8), nt]
         for dst, a, b in ops:
@@ -595,7 +598,7 @@ def simulate(code, nrounds, slots):
             op = code[pos:pos + 9]
             pos += 9
             a, b = comb(op[1:5]), comb(op[5:9])
-            if kind == K_MUL:
+            if kind in (K_MUL, K_MUL4):
                 r = f2_mul(a, b)
             elif kind == K_LIN:
                 r = f2_add(a, b)
