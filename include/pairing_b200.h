@@ -70,7 +70,7 @@ int bls_ctx_trim(bls_ctx*, size_t keep_bytes);
 /* bls_pairing_* / bls_final_exponentiation_* pick between two kernels by batch size: up to these many elements one WARP
  * works on each element (latency path: ~2 ms for one pairing or for a thousand, the crate's bench_pairing_full shape),
  * above them one lane pair does (throughput path: 9.9 ms of latency, 1.37 M pairings/s).  Same bits either way.
- * 0 disables the latency path.  Defaults: 4096 / 4096. */
+ * 0 disables the latency path.  Defaults: 2560 / 2560 (where the two curves cross on a B200). */
 int bls_ctx_set_latency_path_limits(bls_ctx*, size_t max_pairings, size_t max_final_exps);
 
 /* ------------------------------------------------------------------ pairing engine (host buffers) */

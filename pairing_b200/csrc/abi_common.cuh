@@ -71,10 +71,10 @@ struct bls_ctx {
 // Defaults of the two limits: below them one WARP per element (~2 ms for one pairing or for a thousand) beats the lane-pair
 // throughput kernels (9.9 ms of latency, 1.37 M pairings/s); bls_ctx_set_latency_path_limits overrides them per context.
 #ifndef BLS_WIDE_PAIRING_MAX
-#define BLS_WIDE_PAIRING_MAX 4096
+#define BLS_WIDE_PAIRING_MAX 2560
 #endif
 #ifndef BLS_WIDE_FINAL_EXP_MAX
-#define BLS_WIDE_FINAL_EXP_MAX 4096
+#define BLS_WIDE_FINAL_EXP_MAX 2560
 #endif
 
 #define CK(call)                                                                      \

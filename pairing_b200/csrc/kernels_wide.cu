@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(32) k_wide_final_exp(const uint64_t* in, uint6
   const bool all_zero = __all_sync(0xffffffffu, zero);   // mod.rs:107-108: None for f == 0
   wide_load_consts(wide_slots, WIDE_FINAL_EXP_CONST, WIDE_FINAL_EXP_NCONST);
   __syncwarp();
-  wide_run(WIDE_FINAL_EXP_CODE, WIDE_FINAL_EXP_NROUNDS, wide_slots);
+  wide_run(WIDE_FINAL_EXP_CODE, WIDE_FINAL_EXP_NROUNDS, wide_slots, WIDE_FINAL_EXP_NSLOTS);
   if (lp < 6) {
     Fp v = wide_ld(wide_slots, WIDE_FINAL_EXP_OUT[lp], c);
     if (all_zero) v = fp_zero();
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(32) k_wide_pairing(const uint64_t* p, const ui
   else if (lp < 4) wide_st(wide_slots, lp, c, ld_fp(qi + 12 * (lp - 2) + 6 * c));
   wide_load_consts(wide_slots, WIDE_PAIRING_CONST, WIDE_PAIRING_NCONST);
   __syncwarp();
-  wide_run(WIDE_PAIRING_CODE, WIDE_PAIRING_NROUNDS, wide_slots);
+  wide_run(WIDE_PAIRING_CODE, WIDE_PAIRING_NROUNDS, wide_slots, WIDE_PAIRING_NSLOTS);
   if (lp < 6) {
     Fp v = wide_ld(wide_slots, WIDE_PAIRING_OUT[lp], c);
     if (!live) v = (lp == 0 && c == 0) ? fp_one() : fp_zero();     // mod.rs:49-54: the pair is skipped, e = final_exponentiation(one) = one
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(TAIL_TPB, 1) k_pair_product_tail(const uint64_
   const bool all_zero = __all_sync(0xffffffffu, zero);
   wide_load_consts(wide_slots, WIDE_FINAL_EXP_CONST, WIDE_FINAL_EXP_NCONST);
   __syncwarp();
-  wide_run(WIDE_FINAL_EXP_CODE, WIDE_FINAL_EXP_NROUNDS, wide_slots);
+  wide_run(WIDE_FINAL_EXP_CODE, WIDE_FINAL_EXP_NROUNDS, wide_slots, WIDE_FINAL_EXP_NSLOTS);
   if (lp < 6) {
     Fp v = wide_ld(wide_slots, WIDE_FINAL_EXP_OUT[lp], c);
     if (all_zero) v = fp_zero();
@@ -130,16 +130,16 @@ __global__ void __launch_bounds__(TAIL_TPB, 1) k_pair_product_tail(const uint64_
   if (threadIdx.x == 0 && is_some) is_some[0] = !all_zero;
 }
 
-static const size_t TAIL_SMEM = (size_t)(TAIL_LP / 2 * 6 > WIDE_FINAL_EXP_NSLOTS ? TAIL_LP / 2 * 6 : WIDE_FINAL_EXP_NSLOTS) * WIDE_SLOT_BYTES;
+static const size_t TAIL_SMEM = (size_t)(TAIL_LP / 2 * 6 > WIDE_FINAL_EXP_NSLOTS + 1 ? TAIL_LP / 2 * 6 : WIDE_FINAL_EXP_NSLOTS + 1) * WIDE_SLOT_BYTES;
 
 extern "C" {
 int bls_internal_wide_final_exp(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n, cudaStream_t s) {
-  k_wide_final_exp<<<(unsigned)n, 32, WIDE_FINAL_EXP_NSLOTS * WIDE_SLOT_BYTES, s>>>((const uint64_t*)in, (uint64_t*)out, is_some, n);
+  k_wide_final_exp<<<(unsigned)n, 32, (WIDE_FINAL_EXP_NSLOTS + 1) * WIDE_SLOT_BYTES, s>>>((const uint64_t*)in, (uint64_t*)out, is_some, n);
   LAUNCH_CHECK();
   return BLS_OK;
 }
 int bls_internal_wide_pairing(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, cudaStream_t s) {
-  k_wide_pairing<<<(unsigned)n, 32, WIDE_PAIRING_NSLOTS * WIDE_SLOT_BYTES, s>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  k_wide_pairing<<<(unsigned)n, 32, (WIDE_PAIRING_NSLOTS + 1) * WIDE_SLOT_BYTES, s>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
 }

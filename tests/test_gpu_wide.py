@@ -23,9 +23,9 @@ def path_ctx(ctx, request):
     if request.param == "lanepair":
         ctx.set_latency_path_limits(0, 0)
     else:
-        ctx.set_latency_path_limits(4096, 4096)
+        ctx.set_latency_path_limits(2560, 2560)
     yield ctx
-    ctx.set_latency_path_limits(4096, 4096)
+    ctx.set_latency_path_limits(2560, 2560)
 
 
 def test_single_pairing_relic_kat(path_ctx):

@@ -557,14 +557,15 @@ def enc_term(t):
 
 
 def encode(prog):
-    """u16 words: per round [kind | nops << 8, max terms per operand], then per op [dst, 4 A-terms, 4 B-terms]"""
+    """u16 words: per round [kind | nops << 8, max A-terms | max B-terms << 8], then per op [dst, 4 A-terms, 4 B-terms]"""
     code = []
     for kind, ops in prog.rounds:
         k = {"mul": K_MUL, "lin": K_LIN, "inv": K_INV}[kind]
         if kind == "mul" and len(ops) <= W // 2:
             k = K_MUL4          # at most 8 products: FOUR lanes per product, one plain Montgomery product each (wide.cuh)
-        nt = max([max(len(a), len(b)) for _, a, b in ops], default=0)
-        code += [k | (len(ops) << 8), nt]
+        nta = max([len(a) for _, a, b in ops], default=0)       # terms to walk per operand side (maxima over the round's micro-ops)
+        ntb = max([len(b) for _, a, b in ops], default=0)
+        code += [k | (len(ops) << 8), nta | (ntb << 8)]
         for dst, a, b in ops:
             assert len(a) <= 4 and len(b) <= 4
             code += [dst] + [enc_term(t) for t in a] + [NONE] * (4 - len(a)) + [enc_term(t) for t in b] + [NONE] * (4 - len(b))
@@ -628,7 +629,7 @@ def run_program(name, inputs):
 def render(names=("FINAL_EXP", "PAIRING")):
     out = ["// wide_prog_gen.cuh -- GENERATED by tools/wide_gen.py (do not edit; `python tools/wide_gen.py` rewrites it).",
            "// Micro-programs of the warp-cooperative tower engine (wide.cuh): u16 words, per round",
-           "//   [kind | nops << 8, max terms per operand] then per micro-op [dst, 4 A-terms, 4 B-terms];",
+           "//   [kind | nops << 8, max A-terms | max B-terms << 8] then per micro-op [dst, 4 A-terms, 4 B-terms];",
            "//   term = slot | neg << 10 | xi << 11 | log2(multiplier) << 12 | conj << 14, 0xffff = none.",
            "#pragma once", "#include <stdint.h>", ""]
     for name in names:
