@@ -26,6 +26,13 @@ __device__ __forceinline__ void st_p12(uint64_t* p, const P12& a) {
 #ifndef BLS_PAIR_MINB
 #define BLS_PAIR_MINB 2
 #endif
+// The odd pair left over by a trip sequence goes through p12_mul_by_line_pair(.., single) instead of mul_by_014 when the trip
+// count is short (below BLS_MM_SINGLE_VIA_PAIR_BELOW): there the leftover is a seventh of the work and mul_by_014 -- code no other
+// step of the loop executes -- costs 45 % more per product than the pair path (instruction-cache misses); for long trip counts the
+// leftover is negligible and the cheaper 13-product path stays.
+#ifndef BLS_MM_SINGLE_VIA_PAIR_BELOW
+#define BLS_MM_SINGLE_VIA_PAIR_BELOW 32
+#endif
 #ifndef BLS_MM_MINB
 #define BLS_MM_MINB 2      /* blocks per SM of the multi-pairing kernels; 3 (168 registers) measured 3.22 vs 4.87 M pairs/s at 2^20 */
 #endif
@@ -264,7 +271,7 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_MM_MINB) k_pair_multi_miller
       for (size_t j = 0; j < per; j += 2) {          // two pairs at a time: see p12_mul_by_line_pair
         const PLine l = mm_prepared_line(p, qp, n, t + j * T, idx);
         if (j + 1 < per) p12_mul_by_line_pair(f, l, mm_prepared_line(p, qp, n, t + (j + 1) * T, idx));
-        else p12_mul_by_014(f, l.c0, l.c1, l.c4);
+        else if (per < BLS_MM_SINGLE_VIA_PAIR_BELOW) p12_mul_by_line_pair(f, l, l, true); else p12_mul_by_014(f, l.c0, l.c1, l.c4);
       }
       idx++;
     }
@@ -332,18 +339,32 @@ __host__ __device__ __forceinline__ size_t mm_rstate_words(size_t n) { return ((
 #ifndef BLS_MM_STREAM
 #define BLS_MM_STREAM 0
 #endif
+// BLS_MM_STREAM = 2: an explicit L2 evict-first policy on the running-point traffic (createpolicy + cache_hint), L1 left alone
+__device__ __forceinline__ uint64_t mm_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint32_t mm_ld_evict_first(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(mm_evict_first_policy()));
+  return v;
+}
+__device__ __forceinline__ void mm_st_evict_first(uint32_t* p, uint32_t v) {
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(mm_evict_first_policy()) : "memory");
+}
 __device__ __forceinline__ void ld_pjac_blk(PJac& r, const uint32_t* s, size_t pair) {
   uint32_t* w = reinterpret_cast<uint32_t*>(&r);
   const uint32_t* b = s + (pair >> 4) * (36 * 32) + 2 * (pair & 15) + pair_c();
 #pragma unroll
-  for (int k = 0; k < 36; k++) w[k] = BLS_MM_STREAM ? __ldcs(b + k * 32) : b[k * 32];
+  for (int k = 0; k < 36; k++) w[k] = BLS_MM_STREAM == 2 ? mm_ld_evict_first(b + k * 32) : BLS_MM_STREAM ? __ldcs(b + k * 32) : b[k * 32];
 }
 __device__ __forceinline__ void st_pjac_blk(uint32_t* s, size_t pair, const PJac& r) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
   uint32_t* b = s + (pair >> 4) * (36 * 32) + 2 * (pair & 15) + pair_c();
 #pragma unroll
   for (int k = 0; k < 36; k++) {
-    if (BLS_MM_STREAM) __stcs(b + k * 32, w[k]); else b[k * 32] = w[k];
+    if (BLS_MM_STREAM == 2) mm_st_evict_first(b + k * 32, w[k]); else if (BLS_MM_STREAM) __stcs(b + k * 32, w[k]); else b[k * 32] = w[k];
   }
 }
 // one step (phase 0: doubling, phase 1: addition) of pair i's running point, and its line value at P_i
@@ -383,7 +404,7 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_MM_MINB) k_pair_multi_miller
       for (size_t j = 0; j < per; j += 2) {          // two pairs at a time: see p12_mul_by_line_pair
         const PLine l = mm_step_line(p, q, n, rstate, t + j * T, phase, b);
         if (j + 1 < per) p12_mul_by_line_pair(f, l, mm_step_line(p, q, n, rstate, t + (j + 1) * T, phase, b));
-        else p12_mul_by_014(f, l.c0, l.c1, l.c4);
+        else if (per < BLS_MM_SINGLE_VIA_PAIR_BELOW) p12_mul_by_line_pair(f, l, l, true); else p12_mul_by_014(f, l.c0, l.c1, l.c4);
       }
     }
     if (b >= 0) p12_sqr(f, f);

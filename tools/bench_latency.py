@@ -12,6 +12,7 @@ from pairing_b200.device import DeviceEngine
 ap = argparse.ArgumentParser()
 ap.add_argument("--mm-log2", type=int, default=20)
 ap.add_argument("--only-mm", action="store_true")
+ap.add_argument("--mm-sweep", action="store_true")
 args = ap.parse_args()
 eng = DeviceEngine(device=0)
 ctx = eng.ctx
@@ -55,8 +56,20 @@ for cnt in (8, 296):
 nm = 1 << args.mm_log2
 pm = pa.repeat(nm // N, 1).contiguous(); qm = qa.repeat(nm // N, 1).contiguous()
 eng._buf("mm", ctx.multi_miller_scratch_bytes(nm))
-for frac in (1, 2, 4, 8):
+for frac in (() if args.mm_sweep else (1, 2, 4, 8)):
     n = nm // frac
     a = timeit(lambda: eng.multi_miller_loop(pm[:n], qm[:n]), reps=3)
     b = timeit(lambda: eng.pairing_product(pm[:n], qm[:n]), reps=3)
     print("product of 2^%d / %d pairs: multi_miller_loop %.3f ms (%.2f M pairs/s), + final exponentiation %.3f ms" % (args.mm_log2, frac, a, n / a / 1e3, b))
+
+if args.mm_sweep:     # trip counts (pairs per lane pair) 1 .. 14, odd and even, and the 2^20 case
+    T = ctx.sm_count * 2 * 64
+    big = 1 << 20
+    pm = pa.repeat(big // N, 1).contiguous(); qm = qa.repeat(big // N, 1).contiguous()
+    eng._buf("mm", ctx.multi_miller_scratch_bytes(big))
+    for per in ((6, 7, 8, 14) if args.only_mm else (1, 2, 3, 4, 5, 6, 7, 8, 13, 14)):
+        n = T * per
+        a = timeit(lambda: eng.multi_miller_loop(pm[:n], qm[:n]), reps=3)
+        print("trips %2d (n = %7d): multi_miller_loop %8.3f ms  (%.3f ms per trip)" % (per, n, a, a / per))
+    a = timeit(lambda: eng.multi_miller_loop(pm, qm), reps=3)
+    print("n = 2^20: multi_miller_loop %8.3f ms" % a)
