@@ -369,7 +369,14 @@ def run_ours(args):
         k_out = torch.empty((1000, 72), dtype=torch.int64, device=eng.device)
         eng.pairing(pa[:1000].contiguous(), qa[:1000].contiguous(), k_out)
         ms_k, _ = timed(lambda: eng.pairing(pa[:1000].contiguous(), qa[:1000].contiguous(), k_out))
-        secondary["single_pairing"] = {"latency_ms": ms_one, "batch_1000_ms": ms_k, "value": world * 1000 / (ms_k * 1e-3), "unit": "pairings/s",
+        # the crate's bench_pairing_full calls pairing on PROJECTIVE points: into_affine of both arguments inside the call
+        pj1 = g1_jac[:1000].contiguous()
+        qj1 = torch.zeros((1000, 36), dtype=torch.int64, device=eng.device)
+        qj1[:, :24] = qa[:1000, :24]; qj1[:, 24:30] = g1_jac[:1, 12:18]
+        eng.pairing_projective(pj1[:1].contiguous(), qj1[:1].contiguous(), one_out)
+        ms_one_proj, _ = timed(lambda: eng.pairing_projective(pj1[:1].contiguous(), qj1[:1].contiguous(), one_out))
+        ms_k_proj, _ = timed(lambda: eng.pairing_projective(pj1, qj1, k_out))
+        secondary["single_pairing"] = {"latency_ms": ms_one, "batch_1000_ms": ms_k, "projective_inputs_latency_ms": ms_one_proj, "projective_inputs_batch_1000_ms": ms_k_proj, "value": world * 1000 / (ms_k * 1e-3), "unit": "pairings/s",
                                        "units_per_gpu": 1000, "ms": ms_k, "roofline_frac": 1000 / (ms_k * 1e-3) * MAC32_PER_PAIRING / peak_macs,
                                        "config": "configs[0]: one pairing and the 1000 pairings of bench_pairing_full, on the warp-cooperative kernel (one WARP per pairing)"}
         from pairing_b200 import dist as pdist

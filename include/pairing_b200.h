@@ -99,6 +99,10 @@ int bls_pairing_product(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q
 int bls_final_exponentiation_batch(bls_ctx*, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n);
 /* Engine::pairing on affine inputs, lib.rs:101-109 (Miller loop + final exponentiation). */
 int bls_pairing_batch(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n);
+/* Engine::pairing(p, q) with PROJECTIVE arguments (`G1: Into<G1Affine>`, `G2: Into<G2Affine>`, lib.rs:101-109) -- how the crate's
+ * own bench_pairing_full calls it (benches/bls12_381/mod.rs:91-107): the two into_affine conversions (ec.rs:586-619) are fused in
+ * front of the pairing.  A pair with an infinity member gives Fq12::one(). */
+int bls_pairing_projective_batch(bls_ctx*, const bls_g1* p, const bls_g2* q, bls_fq12* out, size_t n);
 /* product of n Fq12 values (Fq12::mul_assign, fq12.rs:116-130): merges per-device partial Miller
  * products before the single final exponentiation of a sharded multi_miller_loop. */
 int bls_fq12_product(bls_ctx*, const bls_fq12* in, size_t n, bls_fq12* out1);
@@ -206,6 +210,7 @@ int bls_miller_loop_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q
 int bls_miller_loop_prepared_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q, bls_fq12* out, size_t n, void* stream);
 int bls_final_exponentiation_dev(bls_ctx*, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n, void* stream);
 int bls_pairing_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, void* stream);
+int bls_pairing_projective_dev(bls_ctx*, const bls_g1* p, const bls_g2* q, bls_fq12* out, size_t n, void* stream);
 /* q1: ONE prepared point in device memory, 16-byte aligned; final_exp != 0 adds the final exponentiation */
 int bls_miller_loop_shared_q_dev(bls_ctx*, const bls_g1_affine* p, const bls_g2_prepared* q1, bls_fq12* out, size_t n, int final_exp, void* stream);
 int bls_fq12_pow_dev(bls_ctx*, const bls_fq12* a, const bls_fr_repr* k, bls_fq12* out, size_t n, void* stream);

@@ -134,6 +134,13 @@ struct Bls12 {
     g.check(bls_multi_miller_loop(g.ctx(), p.data(), q.data(), p.size(), &out));
     return out;
   }
+  // Engine::pairing with projective arguments (Into<G1Affine>, Into<G2Affine>), as bench_pairing_full calls it
+  static std::vector<Fq12> pairing(Gpu& g, const std::vector<G1Point>& p, const std::vector<G2Point>& q) {
+    if (p.size() != q.size()) throw Error(BLS_ERR_INVALID_ARGUMENT, "pairing: length mismatch");
+    std::vector<Fq12> out(p.size());
+    g.check(bls_pairing_projective_batch(g.ctx(), p.data(), q.data(), out.data(), p.size()));
+    return out;
+  }
   // the same ONE miller_loop sharded over several devices
   static Fq12 miller_loop(MultiGpu& g, const std::vector<G1AffinePoint>& p, const std::vector<G2AffinePoint>& q) {
     if (p.size() != q.size()) throw Error(BLS_ERR_INVALID_ARGUMENT, "miller_loop: length mismatch");

@@ -45,7 +45,7 @@ SYMBOLS = [
     "bls_g1_decode_batch", "bls_g2_decode_batch", "bls_g1_encode_batch", "bls_g2_encode_batch",
     "bls_g1_wnaf_table_dev", "bls_g2_wnaf_table_dev", "bls_g1_wnaf_fixed_base_dev", "bls_g2_wnaf_fixed_base_dev",
     "bls_pairing_product", "bls_pairing_product_dev", "bls_fq12_product_tail_dev",
-    "bls_pair_field_op_batch", "bls_pair_field_op_dev",
+    "bls_pair_field_op_batch", "bls_pair_field_op_dev", "bls_pairing_projective_batch", "bls_pairing_projective_dev",
     "bls_mgpu_create", "bls_mgpu_destroy", "bls_mgpu_device_count", "bls_mgpu_ctx", "bls_mgpu_multi_miller_loop",
     "bls_mgpu_pairing_product", "bls_mgpu_pairing_batch", "bls_mgpu_g1_wnaf_mul_batch", "bls_mgpu_g2_wnaf_mul_batch",
     "bls_mgpu_last_phase_ms",
@@ -148,6 +148,8 @@ def load():
         "bls_imad_peak": [vp, ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)],
         "bls_pairing_product": [vp, vp, vp, sz, vp, vp],
         "bls_pair_field_op_batch": [vp, ci, ci, vp, vp, vp, vp, sz],
+        "bls_pairing_projective_batch": [vp, vp, vp, vp, sz],
+        "bls_pairing_projective_dev": [vp, vp, vp, vp, sz, vp],
         "bls_pair_field_op_dev": [vp, ci, ci, vp, vp, vp, vp, sz, vp],
         "bls_pairing_product_dev": [vp, vp, vp, sz, vp, vp, vp, vp],
         "bls_fq12_product_tail_dev": [vp, vp, sz, vp, ci, vp, vp],
@@ -257,6 +259,15 @@ class Context:
 
     def pairing(self, p, q):
         return self._pq(self._lib.bls_pairing_batch, p, q, W_G2A)
+
+    def pairing_projective(self, p, q):
+        """Engine::pairing on Jacobian inputs (the two into_affine conversions fused in front): (n,18),(n,36) -> (n,72)."""
+        p, q = _arr(p, W_G1, "p"), _arr(q, W_G2, "q")
+        if p.shape[0] != q.shape[0]:
+            raise ValueError("p and q must have the same length")
+        out = np.zeros((p.shape[0], W_FQ12), dtype=np.uint64)
+        self._check(self._lib.bls_pairing_projective_batch(self._ctx, _p(p), _p(q), _p(out), p.shape[0]))
+        return out
 
     def _shared_q(self, fn, p, q1):
         p, q1 = _arr(p, W_G1A, "p"), _arr(q1, W_G2P, "q1")

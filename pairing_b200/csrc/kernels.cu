@@ -742,6 +742,28 @@ int bls_internal_product_passes(bls_ctx* ctx, const uint64_t* in, size_t count, 
   }
 }
 
+// Engine::pairing(p, q) with p: Into<G1Affine>, q: Into<G2Affine> on PROJECTIVE inputs (lib.rs:101-109; the crate's bench_pairing_full
+// calls it this way): small batches run the conversions inside the warp-cooperative pairing kernel, large ones convert with
+// k_into_affine into pool-allocated affine rows and run the throughput kernel
+int bls_pairing_projective_dev(bls_ctx* ctx, const bls_g1* p, const bls_g2* q, bls_fq12* out, size_t n, void* stream) {
+  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  USE_DEVICE(ctx);
+  cudaStream_t s = pick(ctx, stream);
+  if (n <= ctx->wide_pairing_max) return bls_internal_wide_pairing_projective(ctx, p, q, out, n, s);
+  void *pa = nullptr, *qa = nullptr;
+  CK(cudaMallocFromPoolAsync(&pa, n * sizeof(bls_g1_affine), ctx->pool, s));
+  cudaError_t e = cudaMallocFromPoolAsync(&qa, n * sizeof(bls_g2_affine), ctx->pool, s);
+  if (e != cudaSuccess) { cudaFreeAsync(pa, s); CK(e); }
+  k_into_affine<Fp><<<blocks_for(n, TPB), TPB, 0, s>>>((const uint64_t*)p, (uint64_t*)pa, n);
+  k_into_affine<Fp2><<<blocks_for(n, TPB), TPB, 0, s>>>((const uint64_t*)q, (uint64_t*)qa, n);
+  ctx->launches += 2;
+  int rc = cudaGetLastError() == cudaSuccess ? bls_pairing_dev(ctx, (const bls_g1_affine*)pa, (const bls_g2_affine*)qa, out, n, stream) : BLS_ERR_CUDA;
+  cudaFreeAsync(pa, s);
+  cudaFreeAsync(qa, s);
+  return rc;
+}
+
 int bls_fq12_product_dev(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq12* out1, void* scratch, void* stream) {
   if (!ctx || !out1 || (n && (!in || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
   USE_DEVICE(ctx);
@@ -892,6 +914,15 @@ static int miller_like(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine
   return run_pipelined(ctx, n, PIPE_CHUNK_PAIRINGS, in, 2, out, sizeof(*out), [&](const void* const* d, void* o, size_t cn) -> int {
     return final_exp ? bls_pairing_dev(ctx, (const bls_g1_affine*)d[0], (const bls_g2_affine*)d[1], (bls_fq12*)o, cn, nullptr)
                      : bls_miller_loop_dev(ctx, (const bls_g1_affine*)d[0], (const bls_g2_affine*)d[1], (bls_fq12*)o, cn, nullptr);
+  });
+}
+int bls_pairing_projective_batch(bls_ctx* ctx, const bls_g1* p, const bls_g2* q, bls_fq12* out, size_t n) {
+  if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
+  if (!n) return BLS_OK;
+  USE_DEVICE(ctx);
+  const PipeIn in[2] = {{p, sizeof(*p)}, {q, sizeof(*q)}};
+  return run_pipelined(ctx, n, PIPE_CHUNK_PAIRINGS, in, 2, out, sizeof(*out), [&](const void* const* d, void* o, size_t cn) -> int {
+    return bls_pairing_projective_dev(ctx, (const bls_g1*)d[0], (const bls_g2*)d[1], (bls_fq12*)o, cn, nullptr);
   });
 }
 int bls_miller_loop_batch(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n) { return miller_like(ctx, p, q, out, n, false); }

@@ -54,6 +54,45 @@ __global__ void __launch_bounds__(32) k_wide_pairing(const uint64_t* p, const ui
   }
 }
 
+// Engine::pairing on PROJECTIVE inputs (the crate's bench_pairing_full: `Bls12::pairing(G1, G2)` converts both points with
+// into_affine first, lib.rs:101-109 + ec.rs:586-619): the TO_AFFINE program (two inversions, eight products) runs in front of
+// the PAIRING program on the same slot file.
+__global__ void __launch_bounds__(32) k_wide_pairing_projective(const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {
+  extern __shared__ __align__(16) uint32_t wide_slots[];
+  const size_t i = blockIdx.x;
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31, lp = lane >> 1, c = lane & 1;
+  const uint64_t* pi = p + G1_W * i;
+  const uint64_t* qi = q + G2_W * i;
+  bool zinf = false;                                   // z == 0: the point at infinity (ec.rs:238-240)
+  if (lp < 3) {                                        // pX, pY, pZ in slots 0..2 (zero u-part)
+    const Fp v = ld_fp(pi + 6 * lp);
+    if (lp == 2) zinf = fp_is_zero(v);
+    wide_st(wide_slots, lp, c, c ? fp_zero() : v);
+  } else if (lp < 6) {                                 // qX, qY, qZ in slots 3..5
+    const Fp v = ld_fp(qi + 12 * (lp - 3) + 6 * c);
+    if (lp == 5) zinf = fp_is_zero(v);
+    wide_st(wide_slots, lp, c, v);
+  }
+  // P is infinity iff lane 4 (pZ, c = 0) saw zero; Q iff both lanes of pair 5 did
+  const unsigned z = __ballot_sync(0xffffffffu, zinf);
+  const bool live = !((z >> 4) & 1u) && !(((z >> 10) & 3u) == 3u);
+  __syncwarp();
+  wide_run(WIDE_TO_AFFINE_CODE, WIDE_TO_AFFINE_NROUNDS, wide_slots, WIDE_TO_AFFINE_NSLOTS);
+  Fp aff = fp_zero();
+  if (lp < 4) aff = wide_ld(wide_slots, WIDE_TO_AFFINE_OUT[lp], c);      // px, py, qx, qy
+  __syncwarp();
+  if (lp < 4) wide_st(wide_slots, lp, c, aff);                           // the PAIRING program's inputs: slots 0..3
+  wide_load_consts(wide_slots, WIDE_PAIRING_CONST, WIDE_PAIRING_NCONST);
+  __syncwarp();
+  wide_run(WIDE_PAIRING_CODE, WIDE_PAIRING_NROUNDS, wide_slots, WIDE_PAIRING_NSLOTS);
+  if (lp < 6) {
+    Fp v = wide_ld(wide_slots, WIDE_PAIRING_OUT[lp], c);
+    if (!live) v = (lp == 0 && c == 0) ? fp_one() : fp_zero();
+    st_fp(out + FQ12_W * i + 12 * lp + 6 * c, v);
+  }
+}
+
 // Product of `count` Fq12 values on lane pairs by ONE block, then (final_exp != 0) the final exponentiation of the
 // product by warp 0 on the wide engine.  Lane pair l multiplies values l, l + 64, ...; the 64 partial products are
 // folded by a shared-memory tree.  Every lane of a warp executes every product (full-mask shuffles inside p2_mul):
@@ -140,6 +179,11 @@ int bls_internal_wide_final_exp(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out,
 }
 int bls_internal_wide_pairing(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, cudaStream_t s) {
   k_wide_pairing<<<(unsigned)n, 32, (WIDE_PAIRING_NSLOTS + 1) * WIDE_SLOT_BYTES, s>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_internal_wide_pairing_projective(bls_ctx* ctx, const bls_g1* p, const bls_g2* q, bls_fq12* out, size_t n, cudaStream_t s) {
+  k_wide_pairing_projective<<<(unsigned)n, 32, (WIDE_PAIRING_NSLOTS + 1) * WIDE_SLOT_BYTES, s>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
 }

@@ -45,6 +45,15 @@ class DeviceEngine:
         self.ctx.call_dev("bls_pairing_dev", p.data_ptr(), q.data_ptr(), out.data_ptr(), n, self._stream())
         return out
 
+    def pairing_projective(self, p, q, out=None):
+        """Engine::pairing on Jacobian rows (n,18),(n,36): into_affine fused in front of the pairing."""
+        _check(p, nat.W_G1, "p"); _check(q, nat.W_G2, "q")
+        n = p.shape[0]
+        if out is None:
+            out = torch.empty((n, nat.W_FQ12), dtype=torch.int64, device=self.device)
+        self.ctx.call_dev("bls_pairing_projective_dev", p.data_ptr(), q.data_ptr(), out.data_ptr(), n, self._stream())
+        return out
+
     def miller_loop_batch(self, p, q, out=None):
         _check(p, nat.W_G1A, "p"); _check(q, nat.W_G2A, "q")
         n = p.shape[0]

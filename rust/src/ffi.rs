@@ -32,6 +32,7 @@ extern "C" {
     pub fn bls_pairing_shared_q_batch(ctx: *mut bls_ctx, p: *const bls_g1_affine, q1: *const bls_g2_prepared, out: *mut bls_fq12, n: usize) -> c_int;
     pub fn bls_multi_miller_loop(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_affine, n: usize, out1: *mut bls_fq12) -> c_int;
     pub fn bls_multi_miller_loop_prepared(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_prepared, n: usize, out1: *mut bls_fq12) -> c_int;
+    pub fn bls_pairing_projective_batch(ctx: *mut bls_ctx, p: *const bls_g1, q: *const bls_g2, out: *mut bls_fq12, n: usize) -> c_int;
     pub fn bls_pairing_product(ctx: *mut bls_ctx, p: *const bls_g1_affine, q: *const bls_g2_affine, n: usize, out1: *mut bls_fq12, is_some: *mut u8) -> c_int;
     pub fn bls_mgpu_create(devices: *const c_int, n_devices: c_int, err: *mut c_int) -> *mut bls_mgpu;
     pub fn bls_mgpu_destroy(m: *mut bls_mgpu);

@@ -45,6 +45,17 @@ impl Gpu {
         Ok(out.iter().map(marshal::fq12_back).collect())
     }
 
+    /// `Bls12::pairing(p_i, q_i)` with projective arguments (`Into<G1Affine>`, `Into<G2Affine>`): conversions fused in front.
+    pub fn pairing_projective_batch(&self, p: &[G1], q: &[G2]) -> Result<Vec<Fq12>, GpuError> {
+        assert_eq!(p.len(), q.len());
+        let pp: Vec<bls_g1> = p.iter().map(marshal::g1).collect();
+        let qq: Vec<bls_g2> = q.iter().map(marshal::g2).collect();
+        let mut out = vec![marshal::FQ12_ZERO; p.len()];
+        let ctx = self.ctx.lock().unwrap();
+        check(unsafe { bls_pairing_projective_batch(*ctx, pp.as_ptr(), qq.as_ptr(), out.as_mut_ptr(), p.len()) }, *ctx)?;
+        Ok(out.iter().map(marshal::fq12_back).collect())
+    }
+
     /// `Bls12::miller_loop(&[(&p_0.prepare(), &q_0.prepare()), ...])`: one shared accumulator (mod.rs:40-102).
     pub fn multi_miller_loop(&self, p: &[G1Affine], q: &[G2Affine]) -> Result<Fq12, GpuError> {
         assert_eq!(p.len(), q.len());

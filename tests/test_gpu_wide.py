@@ -45,6 +45,18 @@ def test_pairing_small_batches(path_ctx, n):
     eq(path_ctx.pairing(p, q), o.pairing(p, q, TH))
 
 
+@pytest.mark.parametrize("n", [1, 5, 130, 1000])
+def test_pairing_on_projective_inputs(path_ctx, n):
+    """Engine::pairing with `Into<G1Affine>` / `Into<G2Affine>` arguments, as the crate's bench_pairing_full calls it: the two
+    into_affine conversions fused in front (non-normalised Z, Z == one and infinity members)"""
+    pj = dg.g1_points(n, 320, infinity_at=(3,) if n > 4 else ())
+    qj = dg.g2_points(n, 321, infinity_at=(4,) if n > 4 else ())
+    if n > 8:                                          # a few already-normalised points (Z == one): the into_affine shortcut, ec.rs:592-596
+        pj[6:8] = o.g1_batch_normalization(pj[6:8]); qj[7:9] = o.g2_batch_normalization(qj[7:9])
+    want = o.pairing(o.g1_into_affine(pj), o.g2_into_affine(qj), TH)
+    eq(path_ctx.pairing_projective(pj, qj), want)
+
+
 def test_final_exponentiation_small_batches(path_ctx):
     f = dg.rand_field(70, 12, 303)
     f[4] = 0                       # None (mod.rs:107-108)

@@ -70,6 +70,19 @@ def test_miller_program_random_pair():
     assert _as12(outs) == m.miller_loop([(p, m.g2_prepare(q))])
 
 
+def test_to_affine_program():
+    """the two into_affine conversions in front of the pairing on projective inputs (ec.rs:586-619)"""
+    rnd = random.Random(13)
+    pj = m.pt_mul(m._F1, m.pt_from_affine(m._F1, m.G1_GEN_AFFINE), rnd.randrange(1, m.R_ORDER))
+    qj = m.pt_mul(m._F2, m.pt_from_affine(m._F2, m.G2_GEN_AFFINE), rnd.randrange(1, m.R_ORDER))
+    pj = m.pt_double(m._F1, pj); qj = m.pt_double(m._F2, qj)              # Z != 1
+    ins = {"pX": (pj[0], 0), "pY": (pj[1], 0), "pZ": (pj[2], 0), "qX": qj[0], "qY": qj[1], "qZ": qj[2]}
+    outs, prog = wg.run_program("TO_AFFINE", ins)
+    pa, qa = m.pt_to_affine(m._F1, pj), m.pt_to_affine(m._F2, qj)
+    assert outs == [(pa[0], 0), (pa[1], 0), qa[0], qa[1]]
+    assert prog.stats["inv"] == 2
+
+
 def test_committed_header_is_current():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "wide_gen.py"), "--check"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr

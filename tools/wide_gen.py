@@ -420,6 +420,23 @@ def build_pairing():
     return g, flat12(final_exponentiation(g, f12_materialize(g, f)))
 
 
+def build_to_affine():
+    """The two into_affine conversions of Engine::pairing on PROJECTIVE inputs (the crate's bench_pairing_full shape,
+    benches/bls12_381/mod.rs:91-107; ec.rs:586-619: x / z^2, y / z^3 -- the z == one shortcut yields the same canonical values).
+    Runs in front of the PAIRING program.  G1 coordinates enter (and leave) as Fq2 values with a zero u-part.
+    Outputs: px, py, qx, qy."""
+    g = Graph()
+    names = ["pX", "pY", "pZ", "qX", "qY", "qZ"]
+    pX, pY, pZ, qX, qY, qZ = [g.input(nm) for nm in names]
+    def to_affine(x, y, z):
+        zi = g.inv(z)
+        zi2 = g.mul(zi, zi)
+        return g.mul(x, zi2), g.mul(y, g.mul(zi2, zi))
+    px, py = to_affine(pX, pY, pZ)
+    qx, qy = to_affine(qX, qY, qZ)
+    return g, [px, py, qx, qy]
+
+
 def build_miller():
     g = Graph()
     g.const(0)
@@ -433,7 +450,8 @@ def build_fq12_mul():
     return g, flat12(f12_mul(g, a, b))
 
 
-PROGRAMS = {"FINAL_EXP": build_final_exp, "PAIRING": build_pairing, "MILLER": build_miller, "FQ12_MUL": build_fq12_mul}
+PROGRAMS = {"FINAL_EXP": build_final_exp, "PAIRING": build_pairing, "TO_AFFINE": build_to_affine, "MILLER": build_miller,
+            "FQ12_MUL": build_fq12_mul}
 
 
 # ------------------------------------------------------------------------------------------------ scheduling
@@ -626,7 +644,7 @@ def run_program(name, inputs):
 
 
 # ------------------------------------------------------------------------------------------------ header
-def render(names=("FINAL_EXP", "PAIRING")):
+def render(names=("FINAL_EXP", "PAIRING", "TO_AFFINE")):
     out = ["// wide_prog_gen.cuh -- GENERATED by tools/wide_gen.py (do not edit; `python tools/wide_gen.py` rewrites it).",
            "// Micro-programs of the warp-cooperative tower engine (wide.cuh): u16 words, per round",
            "//   [kind | nops << 8, max A-terms | max B-terms << 8] then per micro-op [dst, 4 A-terms, 4 B-terms];",
@@ -643,10 +661,10 @@ def render(names=("FINAL_EXP", "PAIRING")):
         out.append("#define WIDE_%s_NSLOTS %d" % (name, prog.nslots))
         out.append("// inputs: " + ", ".join("%s -> slot %d" % (nm, s) for nm, s in prog.inputs))
         out.append("static __device__ const uint16_t WIDE_%s_CONST[][2] = { %s };   // {constant index, slot}"
-                   % (name, ", ".join("{%d, %d}" % (idx, s) for idx, s in prog.consts)))
+                   % (name, ", ".join("{%d, %d}" % (idx, s) for idx, s in prog.consts) or "{0, 0}"))
         out.append("#define WIDE_%s_NCONST %d" % (name, len(prog.consts)))
-        out.append("static __device__ const uint16_t WIDE_%s_OUT[6] = { %s };"
-                   % (name, ", ".join(str(s if s is not None else NONE) for s in prog.outputs)))
+        out.append("static __device__ const uint16_t WIDE_%s_OUT[%d] = { %s };"
+                   % (name, len(prog.outputs), ", ".join(str(s if s is not None else NONE) for s in prog.outputs)))
         out.append("static __device__ const uint16_t WIDE_%s_CODE[%d] = {" % (name, len(code)))
         for i in range(0, len(code), 24):
             out.append("  " + ",".join("%d" % w for w in code[i:i + 24]) + ",")
