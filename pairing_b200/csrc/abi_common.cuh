@@ -65,6 +65,7 @@ struct bls_ctx {
   cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
   cudaMemPool_t pool;                            // staging buffers of the host-buffer entry points: cached across calls
   uint64_t launches;
+  bool mm_smem_ready;                            // kernels_mm.cu: the > 48 KB dynamic shared memory opt-in has been made on this device
   size_t wide_pairing_max, wide_final_exp_max;   // batches up to these sizes run on the warp-cooperative engine (kernels_wide.cu)
   char last_error[256];
 };

@@ -612,6 +612,7 @@ bls_ctx* bls_ctx_create(int device, int* err) {
   if (!ctx) { if (err) *err = BLS_ERR_OUT_OF_MEMORY; return nullptr; }
   ctx->device = device;
   ctx->launches = 0;
+  ctx->mm_smem_ready = false;
   ctx->wide_pairing_max = BLS_WIDE_PAIRING_MAX;
   ctx->wide_final_exp_max = BLS_WIDE_FINAL_EXP_MAX;
   ctx->last_error[0] = 0;

@@ -1,41 +1,9 @@
 // kernels_pair.cu -- the pairing engine on LANE PAIRS (pair_tower.cuh): Miller loops, final exponentiation, the fused
-// pairing kernel, G2Prepared, multi-pairing Miller loop, GT powers, and their device-pointer entry points.
+// pairing kernel, G2Prepared, GT powers, and their device-pointer entry points (the multi-pairing Miller loop: kernels_mm.cu).
 // Its own translation unit: see abi_common.cuh.
-#include "abi_common.cuh"
-#include "pair_tower.cuh"
 
-// ---- lane-pair kernels (pair_tower.cuh): two adjacent lanes per pairing, lane c owns coefficient c
-// of every Fq2.  Threads past the end of the batch recompute the last element (every lane has to
-// reach every shuffle) and skip the store.
-__device__ __forceinline__ P2 ld_p2(const uint64_t* p) { return P2{ld_fp(p + 6 * pair_c())}; }
-__device__ __forceinline__ void st_p2(uint64_t* p, const P2& a) { st_fp(p + 6 * pair_c(), a.v); }
-__device__ __forceinline__ void ld_p12(P12& r, const uint64_t* p) {
-  r.c0.c0 = ld_p2(p); r.c0.c1 = ld_p2(p + 12); r.c0.c2 = ld_p2(p + 24);
-  r.c1.c0 = ld_p2(p + 36); r.c1.c1 = ld_p2(p + 48); r.c1.c2 = ld_p2(p + 60);
-}
-__device__ __forceinline__ void st_p12(uint64_t* p, const P12& a) {
-  st_p2(p, a.c0.c0); st_p2(p + 12, a.c0.c1); st_p2(p + 24, a.c0.c2);
-  st_p2(p + 36, a.c1.c0); st_p2(p + 48, a.c1.c1); st_p2(p + 60, a.c1.c2);
-}
+#include "pair_io.cuh"
 
-// launch shape of the lane-pair kernels: BLS_PAIR_TPB threads per block, BLS_PAIR_MINB blocks per SM
-// (registers per thread <= 65536 / (TPB * MINB)).  Small blocks keep the tail of a 2^16 batch short.
-#ifndef BLS_PAIR_TPB
-#define BLS_PAIR_TPB 128
-#endif
-#ifndef BLS_PAIR_MINB
-#define BLS_PAIR_MINB 2
-#endif
-// The odd pair left over by a trip sequence goes through p12_mul_by_line_pair(.., single) instead of mul_by_014 when the trip
-// count is short (below BLS_MM_SINGLE_VIA_PAIR_BELOW): there the leftover is a seventh of the work and mul_by_014 -- code no other
-// step of the loop executes -- costs 45 % more per product than the pair path (instruction-cache misses); for long trip counts the
-// leftover is negligible and the cheaper 13-product path stays.
-#ifndef BLS_MM_SINGLE_VIA_PAIR_BELOW
-#define BLS_MM_SINGLE_VIA_PAIR_BELOW 32
-#endif
-#ifndef BLS_MM_MINB
-#define BLS_MM_MINB 2      /* blocks per SM of the multi-pairing kernels; 3 (168 registers) measured 3.22 vs 4.87 M pairs/s at 2^20 */
-#endif
 // BLS_PAIR_SMEM = 1 keeps the Miller accumulator f and the running G2 point R of every lane in shared memory (an odd
 // number of words per lane: conflict-free 32-bit accesses) instead of the per-thread stack.
 #ifndef BLS_PAIR_SMEM
@@ -80,16 +48,6 @@ template <bool FE> static cudaError_t pair_miller_smem_optin() {
   return cudaFuncSetAttribute(k_pair_miller<FE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_miller_smem_bytes());
 }
 
-__device__ __forceinline__ void pcoeffs_set_one_if(bool dead, PCoeffs& c) {
-  const P2 one = p2_one(), zero = p2_zero();
-  c.c0.v = fp_select(dead, zero.v, c.c0.v);
-  c.c1.v = fp_select(dead, zero.v, c.c1.v);
-  c.c2.v = fp_select(dead, one.v, c.c2.v);
-}
-
-// G2Prepared::from_affine (mod.rs:168-358) on lane pairs: lane c writes coefficient c of every Fq2 of the 68 triples
-__device__ __forceinline__ void st_pcoeffs(uint64_t* p, const PCoeffs& c) { st_p2(p, c.c0); st_p2(p + 12, c.c1); st_p2(p + 24, c.c2); }
-__device__ __forceinline__ void ld_pcoeffs(PCoeffs& c, const uint64_t* p) { c.c0 = ld_p2(p); c.c1 = ld_p2(p + 12); c.c2 = ld_p2(p + 24); }
 __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_g2_prepare(const uint64_t* q, uint64_t* out, size_t n) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = t >> 1;
@@ -213,74 +171,6 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_miller_sha
   }
 }
 
-// One partial product per BLOCK: the 64 lane pairs of a block fold their accumulators by a shared-memory tree (6 levels of
-// Fq12 products) and lane pair 0 stores the result -- 296 partials per launch instead of 18 944, so that ONE small tail
-// kernel (kernels_wide.cu: k_pair_product_tail) finishes the product.  Whole warps only: below 16 lane pairs the other lane
-// pairs of warp 0 multiply along (every lane of a warp has to reach the shuffles inside p2_mul); their results are unused.
-#define MM_LP (BLS_PAIR_TPB / 2)
-__device__ __forceinline__ void mm_block_reduce_store(P12& f, uint64_t* partial) {
-  __shared__ uint32_t s_tree[(MM_LP / 2) * 144];       // at level s the lane pairs [s, 2s) publish, the lane pairs [0, s) multiply
-  const int lp = threadIdx.x >> 1;
-#pragma unroll 1
-  for (int s = MM_LP / 2; s >= 1; s >>= 1) {
-    __syncthreads();
-    if (lp >= s && lp < 2 * s) {
-      uint32_t* dst = s_tree + (lp - s) * 144 + pair_c() * 72;
-      const uint32_t* w = reinterpret_cast<const uint32_t*>(&f);
-#pragma unroll
-      for (int k = 0; k < 72; k++) dst[k] = w[k];
-    }
-    __syncthreads();
-    if (lp < (s < 16 ? 16 : s)) {
-      P12 x;
-      const uint32_t* src = s_tree + lp * 144 + pair_c() * 72;
-      uint32_t* w = reinterpret_cast<uint32_t*>(&x);
-#pragma unroll
-      for (int k = 0; k < 72; k++) w[k] = src[k];
-      p12_mul(f, f, x);
-    }
-  }
-  if (lp == 0) st_p12(partial, f);
-}
-
-// ONE miller_loop over n prepared pairs: lane pair t owns pairs t, t+T, ... and one accumulator (see k_pair_multi_miller)
-__device__ __forceinline__ PLine mm_prepared_line(const uint64_t* p, const uint64_t* qp, size_t n, size_t i, int idx) {
-  const bool in_range = i < n;
-  if (!in_range) i = n - 1;
-  const uint64_t* pi = p + G1A_W * i;
-  const uint64_t* qi = qp + (size_t)G2P_W * i;
-  const bool dead = !in_range || pi[12] != 0 || qi[G2P_W - 1] != 0;
-  PCoeffs c;
-  ld_pcoeffs(c, qi + 36 * idx);
-  pcoeffs_set_one_if(dead, c);
-  return p_line(c, ld_fp(pi), ld_fp(pi + 6));
-}
-__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_MM_MINB) k_pair_multi_miller_prepared(const uint64_t* p, const uint64_t* qp, size_t n, uint64_t* partials) {
-  const size_t T = ((size_t)gridDim.x * blockDim.x) >> 1;
-  const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-  const size_t per = (n + T - 1) / T;
-  P12 f;
-  p12_one(f);
-  int idx = 0;
-#pragma unroll 1
-  for (int b = BLS_LOOP_TOP; b >= -1; b--) {
-    const bool bit = b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull);
-#pragma unroll 1
-    for (int rep = 0; rep < (bit ? 2 : 1); rep++) {
-#pragma unroll 1
-      for (size_t j = 0; j < per; j += 2) {          // two pairs at a time: see p12_mul_by_line_pair
-        const PLine l = mm_prepared_line(p, qp, n, t + j * T, idx);
-        if (j + 1 < per) p12_mul_by_line_pair(f, l, mm_prepared_line(p, qp, n, t + (j + 1) * T, idx));
-        else if (per < BLS_MM_SINGLE_VIA_PAIR_BELOW) p12_mul_by_line_pair(f, l, l, true); else p12_mul_by_014(f, l.c0, l.c1, l.c4);
-      }
-      idx++;
-    }
-    if (b >= 0) p12_sqr(f, f);
-  }
-  p12_conjugate(f);
-  mm_block_reduce_store(f, partials + FQ12_W * blockIdx.x);
-}
-
 __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_final_exp(const uint64_t* in, uint64_t* out, uint8_t* is_some, size_t n) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = t >> 1;
@@ -319,98 +209,6 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_fq12_pow(c
     p12_mul(res, res, tbl[nib]);
   }
   if (active) st_p12(out + FQ12_W * i, res);
-}
-
-// Lane-pair form of the multi-pairing Miller loop (the production path of bls_multi_miller_loop*):
-// lane pair t owns pairs t, t+T, ... and ONE accumulator f.  Lane c keeps coefficient c of the running
-// G2 point R_j in the scratch array `rstate` (layout: ld_pjac_blk).
-// Every lane has to reach every shuffle, so there is no `continue`: a pair with an infinity member
-// (mod.rs:49-54) or past the end of the batch multiplies f by the sparse element (1, 0, 0) = one instead,
-// which leaves the canonical value of f unchanged.
-// Scratch layout of the running points: blocks of 16 consecutive pairs (the 16 lane pairs of a warp work on 16 consecutive
-// pairs in every trip: T is a multiple of 64), 36 lines of 128 bytes per block; line k holds word k of both coefficients
-// of the 16 pairs in lane order, so every load / store instruction of a warp moves exactly one full line and a step
-// touches one contiguous 4608-byte block.  (A word-major array over all n -- plane stride n words -- measured bimodal,
-// 222 or 252 ms per 2^20 pairs from one process to the next.)
-__host__ __device__ __forceinline__ size_t mm_rstate_words(size_t n) { return ((n + 15) / 16) * (36 * 32); }
-// BLS_MM_STREAM = 1 marks these accesses evict-first (ld.global.cs / st.global.cs): the 302 MB of running points of a 2^20
-// batch stream through L2 once per loop iteration and compete with the 62 MB of local memory the kernel keeps there.
-// Unmeasured (default off): an A/B candidate for the two timing modes described in DESIGN.md section 4.
-#ifndef BLS_MM_STREAM
-#define BLS_MM_STREAM 0
-#endif
-// BLS_MM_STREAM = 2: an explicit L2 evict-first policy on the running-point traffic (createpolicy + cache_hint), L1 left alone
-__device__ __forceinline__ uint64_t mm_evict_first_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
-}
-__device__ __forceinline__ uint32_t mm_ld_evict_first(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(mm_evict_first_policy()));
-  return v;
-}
-__device__ __forceinline__ void mm_st_evict_first(uint32_t* p, uint32_t v) {
-  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(mm_evict_first_policy()) : "memory");
-}
-__device__ __forceinline__ void ld_pjac_blk(PJac& r, const uint32_t* s, size_t pair) {
-  uint32_t* w = reinterpret_cast<uint32_t*>(&r);
-  const uint32_t* b = s + (pair >> 4) * (36 * 32) + 2 * (pair & 15) + pair_c();
-#pragma unroll
-  for (int k = 0; k < 36; k++) w[k] = BLS_MM_STREAM == 2 ? mm_ld_evict_first(b + k * 32) : BLS_MM_STREAM ? __ldcs(b + k * 32) : b[k * 32];
-}
-__device__ __forceinline__ void st_pjac_blk(uint32_t* s, size_t pair, const PJac& r) {
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(&r);
-  uint32_t* b = s + (pair >> 4) * (36 * 32) + 2 * (pair & 15) + pair_c();
-#pragma unroll
-  for (int k = 0; k < 36; k++) {
-    if (BLS_MM_STREAM == 2) mm_st_evict_first(b + k * 32, w[k]); else if (BLS_MM_STREAM) __stcs(b + k * 32, w[k]); else b[k * 32] = w[k];
-  }
-}
-// one step (phase 0: doubling, phase 1: addition) of pair i's running point, and its line value at P_i
-__device__ __forceinline__ PLine mm_step_line(const uint64_t* p, const uint64_t* q, size_t n, uint32_t* rstate, size_t i, int phase, int b) {
-  const bool in_range = i < n;
-  if (!in_range) i = n - 1;
-  const uint64_t* pi = p + G1A_W * i;
-  const uint64_t* qi = q + G2A_W * i;
-  const bool dead = !in_range || pi[12] != 0 || qi[24] != 0;
-  PJac r;
-  PCoeffs c;
-  if (phase == 0) {
-    if (b == BLS_LOOP_TOP) { r.x = ld_p2(qi); r.y = ld_p2(qi + 12); r.z = p2_one(); }
-    else ld_pjac_blk(r, rstate, i);
-    pg2_doubling_step(r, c);
-    if (b >= 0 && in_range) st_pjac_blk(rstate, i, r);
-  } else {
-    ld_pjac_blk(r, rstate, i);
-    pg2_addition_step(r, ld_p2(qi), ld_p2(qi + 12), c);
-    if (in_range) st_pjac_blk(rstate, i, r);
-  }
-  pcoeffs_set_one_if(dead, c);
-  return p_line(c, ld_fp(pi), ld_fp(pi + 6));
-}
-__global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_MM_MINB) k_pair_multi_miller(const uint64_t* p, const uint64_t* q, size_t n, uint32_t* rstate, uint64_t* partials) {
-  const size_t T = ((size_t)gridDim.x * blockDim.x) >> 1;                       // lane pairs
-  const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-  const size_t per = (n + T - 1) / T;                                            // loop trips, uniform over the grid
-  P12 f;
-  p12_one(f);
-#pragma unroll 1
-  for (int b = BLS_LOOP_TOP; b >= -1; b--) {   // b == -1 is the trailing doubling step (mod.rs:92-94)
-    const bool bit = b >= 0 && ((BLS_LOOP_BITS >> b) & 1ull);
-#pragma unroll 1
-    for (int phase = 0; phase < (bit ? 2 : 1); phase++) {
-#pragma unroll 1
-      for (size_t j = 0; j < per; j += 2) {          // two pairs at a time: see p12_mul_by_line_pair
-        const PLine l = mm_step_line(p, q, n, rstate, t + j * T, phase, b);
-        if (j + 1 < per) p12_mul_by_line_pair(f, l, mm_step_line(p, q, n, rstate, t + (j + 1) * T, phase, b));
-        else if (per < BLS_MM_SINGLE_VIA_PAIR_BELOW) p12_mul_by_line_pair(f, l, l, true); else p12_mul_by_014(f, l.c0, l.c1, l.c4);
-      }
-    }
-    if (b >= 0) p12_sqr(f, f);
-  }
-  p12_conjugate(f);
-  mm_block_reduce_store(f, partials + FQ12_W * blockIdx.x);
 }
 
 // Field-tower operations ON LANE PAIRS (pair_tower.cuh -- the code the pairing kernels run), element-wise, for parity
@@ -556,41 +354,6 @@ int bls_fq12_pow_dev(bls_ctx* ctx, const bls_fq12* a, const bls_fr_repr* k, bls_
   LAUNCH_CHECK();
   return BLS_OK;
 }
-// lane pairs (= partial products) used by the multi-Miller kernel for n pairs: enough pairs per lane pair to
-// amortise the shared squarings, never more lane pairs than pairs; a multiple of the 64 lane pairs of a block
-static size_t mm_threads(const bls_ctx* ctx, size_t n) {
-  const size_t per_block = BLS_PAIR_TPB / 2;
-  size_t full = (size_t)ctx->sm_count * BLS_MM_MINB * per_block;
-  size_t t = n < full ? n : full;
-  t = (t + per_block - 1) / per_block * per_block;
-  return t ? t : per_block;
-}
-size_t bls_multi_miller_scratch_bytes(const bls_ctx* ctx, size_t n) {
-  if (!ctx) return 0;
-  size_t T = mm_threads(ctx, n);
-  return mm_rstate_words(n) * sizeof(uint32_t) + (T / MM_LP) * sizeof(bls_fq12);
-}
-
-// mod.rs:40-102 over ONE n-pair call: the Miller kernel leaves one partial product per block, the tail kernel folds them
-// (and, for bls_pairing_product_dev, runs the single final exponentiation on the warp-cooperative engine)
-static int multi_miller_impl(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, void* scratch, void* stream, int final_exp, uint8_t* is_some) {
-  if (!ctx || !out1 || (n && (!p || !q || !scratch))) return BLS_ERR_INVALID_ARGUMENT;
-  USE_DEVICE(ctx);
-  cudaStream_t s = pick(ctx, stream);
-  if (n == 0) return bls_internal_product_tail(ctx, nullptr, 0, out1, final_exp, is_some, s);   // the empty product: one
-  size_t T = mm_threads(ctx, n);
-  uint32_t* rstate = (uint32_t*)scratch;
-  uint64_t* partials = (uint64_t*)((char*)scratch + mm_rstate_words(n) * sizeof(uint32_t));
-  k_pair_multi_miller<<<(unsigned)(T / MM_LP), BLS_PAIR_TPB, 0, s>>>((const uint64_t*)p, (const uint64_t*)q, n, rstate, partials);
-  LAUNCH_CHECK();
-  return bls_internal_product_tail(ctx, (const bls_fq12*)partials, T / MM_LP, out1, final_exp, is_some, s);
-}
-int bls_multi_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, void* scratch, void* stream) {
-  return multi_miller_impl(ctx, p, q, n, out1, scratch, stream, 0, nullptr);
-}
-int bls_pairing_product_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, size_t n, bls_fq12* out1, uint8_t* is_some, void* scratch, void* stream) {
-  return multi_miller_impl(ctx, p, q, n, out1, scratch, stream, 1, is_some);
-}
 int bls_fq12_product_tail_dev(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq12* out1, int final_exp, uint8_t* is_some, void* stream) {
   if (!ctx || !out1 || (n && !in)) return BLS_ERR_INVALID_ARGUMENT;
   USE_DEVICE(ctx);
@@ -598,11 +361,3 @@ int bls_fq12_product_tail_dev(bls_ctx* ctx, const bls_fq12* in, size_t n, bls_fq
 }
 
 }  // extern "C"
-
-size_t bls_internal_mm_lane_pairs(const bls_ctx* ctx, size_t n) { return mm_threads(ctx, n) / MM_LP; }   // = partial products (one per block)
-int bls_internal_multi_miller_prepared(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* qp, size_t n, bls_fq12* partials, cudaStream_t s) {
-  const size_t T = mm_threads(ctx, n);
-  k_pair_multi_miller_prepared<<<(unsigned)(T / MM_LP), BLS_PAIR_TPB, 0, s>>>((const uint64_t*)p, (const uint64_t*)qp, n, (uint64_t*)partials);
-  LAUNCH_CHECK();
-  return BLS_OK;
-}

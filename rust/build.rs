@@ -12,7 +12,7 @@ fn main() {
     // four translation units: the lane-pair pairing engine and the warp-cooperative engine are compiled on their own
     // (pairing_b200/csrc/abi_common.cuh); mgpu.cu is the host-side multi-device layer
     let mut objs = Vec::new();
-    for unit in &["kernels", "kernels_pair", "kernels_wide", "mgpu"] {
+    for unit in &["kernels", "kernels_pair", "kernels_mm", "kernels_wide", "mgpu"] {
         let src = root.join(format!("pairing_b200/csrc/{}.cu", unit));
         let obj = out.join(format!("{}.o", unit));
         let status = Command::new(&nvcc)
@@ -33,7 +33,7 @@ fn main() {
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
     println!("cargo:rustc-link-lib=dylib=pthread");
-    for f in &["kernels.cu", "kernels_pair.cu", "kernels_wide.cu", "mgpu.cu", "abi_common.cuh", "fr.cuh", "fp.cuh", "fp_sqr_gen.cuh", "tower.cuh", "curve.cuh",
+    for f in &["kernels.cu", "kernels_pair.cu", "kernels_mm.cu", "kernels_wide.cu", "mgpu.cu", "abi_common.cuh", "pair_io.cuh", "fr.cuh", "fp.cuh", "fp_sqr_gen.cuh", "tower.cuh", "curve.cuh",
                "pair_tower.cuh", "wide.cuh", "wide_prog_gen.cuh", "codec.cuh", "constants.cuh"] {
         println!("cargo:rerun-if-changed={}", root.join("pairing_b200/csrc").join(f).display());
     }

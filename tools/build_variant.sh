@@ -19,6 +19,8 @@ fi
 wait
 [ -f _obj/kernels_wide.o ] || $NVCC $FLAGS -c -o _obj/kernels_wide.o kernels_wide.cu
 [ -f _obj/mgpu.o ] || $NVCC $FLAGS -c -o _obj/mgpu.o mgpu.cu
-$NVCC $ARCH -shared -o ../lib/exp_$name.so $KOBJ _obj/$name/kernels_pair.o _obj/kernels_wide.o _obj/mgpu.o -lpthread
+# the multi-pairing unit takes the same extra flags as the pairing unit
+$NVCC $FLAGS $pflags -c -o _obj/$name/kernels_mm.o kernels_mm.cu
+$NVCC $ARCH -shared -o ../lib/exp_$name.so $KOBJ _obj/$name/kernels_pair.o _obj/$name/kernels_mm.o _obj/kernels_wide.o _obj/mgpu.o -lpthread
 echo "built pairing_b200/lib/exp_$name.so"
 cuobjdump --dump-resource-usage ../lib/exp_$name.so 2>/dev/null | grep -A1 "k_pair_millerILb1\|k_pair_multi_millerPK" | grep -o "Function [^:]*\|REG:[0-9]*\|STACK:[0-9]*\|SHARED:[0-9]*" | paste - - - -
