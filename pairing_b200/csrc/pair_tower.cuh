@@ -44,8 +44,9 @@ __device__ __forceinline__ P2 p2_dbl(const P2& a) { return P2{fp_dbl(a.v)}; }
 __device__ __forceinline__ P2 p2_neg(const P2& a) { return P2{fp_neg(a.v)}; }
 // both lanes learn whether the Fq2 value is zero
 __device__ __forceinline__ bool p2_is_zero(const P2& a) {
-  bool z = fp_is_zero(a.v);
-  return z && __shfl_xor_sync(0xffffffffu, (int)z, 1);
+  const bool z = fp_is_zero(a.v);
+  const int zo = __shfl_xor_sync(0xffffffffu, (int)z, 1);      // unconditionally: `z && shfl(..)` would keep lanes with z == false out of the shuffle
+  return z && zo;
 }
 // x (1 + u) = (c0 - c1) + (c0 + c1) u   (fq2.rs:41-45)
 __device__ __forceinline__ P2 p2_mul_by_nonresidue(P2 a) {
@@ -77,7 +78,7 @@ static __device__ __noinline__ bool p2_inv(P2& out, const P2& a) {
   Fp sq = fp_sqr(a.v);
   Fp t = fp_add(sq, pair_xchg(sq));
   Fp ti;
-  bool ok = fp_inv(ti, t);
+  bool ok = fp_inv(ti, t);       // lanes diverge inside (variable-time division steps) and re-converge at the next shuffle
   Fp r = fp_mul(a.v, ti);
   out.v = fp_select(pair_c() == 0, r, fp_neg(r));
   return ok;
@@ -390,11 +391,93 @@ static __device__ __noinline__ void p12_exp_by_x(P12& out, const P12& a, uint64_
   out = res;
 }
 
+// exp_by_x on COMPRESSED cyclotomic elements (Karabina, "Squaring in cyclotomic subgroups", Math. Comp. 2013).  With
+// Fq12 = Fq4[w]/(w^3 - s), Fq4 = Fq2[s]/(s^2 - xi) the element is G0 + G1 w + G2 w^2 with G0 = (c0.c0, c1.c1),
+// G1 = (c1.c0, c0.c2), G2 = (c0.c1, c1.c2), and the Granger-Scott squaring above computes the new G1, G2 from the old
+// G1, G2 alone: dropping G0 leaves two Fq4 squarings -- FOUR Fq2 products per squaring instead of six.  G0 is recovered
+// when a power is needed in full:
+//   g1 = (xi g5^2 + 3 g4^2 - 2 g3) / (4 g2),   g0 = (2 g1^2 + g2 g5 - 3 g3 g4) xi + 1
+// (g2 = c1.c0, g3 = c0.c2, g4 = c0.c1, g5 = c1.c2, g0 = c0.c0, g1 = c1.c1).  The exponent is walked from its LOW end:
+// the powers a^(2^b) of the set bits b are kept compressed, decompressed together (one Fq2 inversion for all of them,
+// Montgomery's trick) and multiplied -- as many Fq12 products as the square-and-multiply of lib.rs:306-324 needs, the
+// same field value, hence the same canonical output.  A zero denominator (g2 = 0: the element one, e.g. a pair with a
+// point at infinity) cannot be decompressed this way: the warp then also runs the uncompressed p12_exp_by_x and the
+// lane pairs concerned take its result (warp-uniform control flow: every lane reaches every shuffle).
+struct PK4 { P2 g2, g3, g4, g5; };
+static __device__ __noinline__ void pk4_sqr(PK4& c) {
+  P2 t2, t3, t4, t5;
+  p4_sqr(t2, t3, c.g2, c.g3);
+  p4_sqr(t4, t5, c.g4, c.g5);
+  const P2 x5 = p2_mul_by_nonresidue(t5);
+  P2 z2 = p2_add(x5, c.g2); z2 = p2_add(p2_dbl(z2), x5);
+  P2 z3 = p2_sub(t4, c.g3); z3 = p2_add(p2_dbl(z3), t4);
+  P2 z4 = p2_sub(t2, c.g4); z4 = p2_add(p2_dbl(z4), t2);
+  P2 z5 = p2_add(t3, c.g5); z5 = p2_add(p2_dbl(z5), t3);
+  c.g2 = z2; c.g3 = z3; c.g4 = z4; c.g5 = z5;
+}
+#define BLS_PK4_MAX 6      /* set bits above bit 0 of |x| = 0xd201000000010000 and of |x| >> 1 */
+static __device__ __noinline__ void p12_exp_by_x_compressed(P12& out, const P12& a, uint64_t x) {
+  PK4 pts[BLS_PK4_MAX];
+  P2 pre[BLS_PK4_MAX];
+  PK4 c{a.c1.c0, a.c0.c2, a.c0.c1, a.c1.c2};
+  const int top = 63 - __clzll((long long)x);
+  int k = 0;
+#pragma unroll 1
+  for (int b = 1; b <= top; b++) {
+    pk4_sqr(c);
+    if ((x >> b) & 1ull) {
+      pts[k] = c;
+      const P2 den = p2_dbl(p2_dbl(c.g2));
+      pre[k] = k ? p2_mul(pre[k - 1], den) : den;            // prefix products of the denominators 4 g2
+      k++;
+    }
+  }
+  const bool bad = p2_is_zero(pre[k - 1]);
+  P2 inv;
+  p2_inv(inv, pre[k - 1]);
+  P12 res;
+#pragma unroll 1
+  for (int i = k - 1; i >= 0; i--) {
+    const PK4 g = pts[i];
+    P2 dinv = inv;
+    if (i) { dinv = p2_mul(inv, pre[i - 1]); inv = p2_mul(inv, p2_dbl(p2_dbl(g.g2))); }
+    const P2 s4 = p2_sqr(g.g4);
+    const P2 num = p2_sub(p2_add(p2_mul_by_nonresidue(p2_sqr(g.g5)), p2_add(p2_dbl(s4), s4)), p2_dbl(g.g3));
+    const P2 g1 = p2_mul(num, dinv);
+    const P2 m34 = p2_mul(g.g3, g.g4);
+    const P2 t = p2_sub(p2_add(p2_dbl(p2_sqr(g1)), p2_mul(g.g2, g.g5)), p2_add(p2_dbl(m34), m34));
+    P12 e;
+    e.c0.c0 = p2_add(p2_mul_by_nonresidue(t), p2_one());
+    e.c0.c1 = g.g4; e.c0.c2 = g.g3;
+    e.c1.c0 = g.g2; e.c1.c1 = g1; e.c1.c2 = g.g5;
+    if (i == k - 1) res = e; else p12_mul(res, res, e);
+  }
+  if (x & 1ull) p12_mul(res, res, a);
+  p12_conjugate(res);
+  if (__any_sync(0xffffffffu, bad)) {
+    P12 alt;
+    p12_exp_by_x(alt, a, x);
+    p12_select(res, bad, alt, res);
+  }
+  out = res;
+}
+#ifndef BLS_EXP_COMPRESSED
+#define BLS_EXP_COMPRESSED 1
+#endif
+__device__ __forceinline__ void p12_exp_by_x_hard(P12& out, const P12& a, uint64_t x) {
+#if BLS_EXP_COMPRESSED
+  p12_exp_by_x_compressed(out, a, x);
+#else
+  p12_exp_by_x(out, a, x);
+#endif
+}
+
 // both lanes learn whether the Fq12 value is zero
 __device__ __forceinline__ bool p12_is_zero(const P12& a) {
   bool z = fp_is_zero(a.c0.c0.v) && fp_is_zero(a.c0.c1.v) && fp_is_zero(a.c0.c2.v) &&
            fp_is_zero(a.c1.c0.v) && fp_is_zero(a.c1.c1.v) && fp_is_zero(a.c1.c2.v);
-  return z && __shfl_xor_sync(0xffffffffu, (int)z, 1);
+  const int zo = __shfl_xor_sync(0xffffffffu, (int)z, 1);
+  return z && zo;
 }
 
 // mod.rs:104-160
@@ -408,22 +491,22 @@ __device__ __forceinline__ bool p_final_exponentiation(P12& out, const P12& in) 
   p12_mul(r, r, f2);
   const uint64_t x = BLS_X_ABS;
   P12 y0, y1, y2, y3;
-  p12_sqr(y0, r);
-  p12_exp_by_x(y1, y0, x);
-  p12_exp_by_x(y2, y1, x >> 1);
+  p12_cyclotomic_sqr(y0, r);          // r is in the cyclotomic subgroup after the easy part: the same value as `square`
+  p12_exp_by_x_hard(y1, y0, x);
+  p12_exp_by_x_hard(y2, y1, x >> 1);
   y3 = r; p12_conjugate(y3);
   p12_mul(y1, y1, y3);
   p12_conjugate(y1);
   p12_mul(y1, y1, y2);
-  p12_exp_by_x(y2, y1, x);
-  p12_exp_by_x(y3, y2, x);
+  p12_exp_by_x_hard(y2, y1, x);
+  p12_exp_by_x_hard(y3, y2, x);
   p12_conjugate(y1);
   p12_mul(y3, y3, y1);
   p12_conjugate(y1);
   p12_frobenius(y1, y1, 3);
   p12_frobenius(y2, y2, 2);
   p12_mul(y1, y1, y2);
-  p12_exp_by_x(y2, y3, x);
+  p12_exp_by_x_hard(y2, y3, x);
   p12_mul(y2, y2, y0);
   p12_mul(y2, y2, r);
   p12_mul(y1, y1, y2);

@@ -7,6 +7,7 @@
 #pragma once
 #include "constants.cuh"
 #include "fp.cuh"
+#include "fp_inv_gcd.cuh"
 
 namespace bls {
 
@@ -49,9 +50,21 @@ static __device__ __noinline__ Fp2 fp2_sqr(Fp2 a) {
 // Fq2 x Fq (the `ell` scalings, mod.rs:61-65)
 __device__ __forceinline__ Fp2 fp2_mul_fp(const Fp2& a, const Fp& s) { return Fp2{fp_mul(a.c0, s), fp_mul(a.c1, s)}; }
 
-// a^(q-2) by a fixed 4-bit window over the (compile-time) exponent.  Value-identical to the
-// reference's binary extended Euclid (fq.rs:849-902): the inverse in a field is unique and the
-// result is canonical.  Returns false (and zero) for a == 0, the reference's `None`.
+// Fq inversion (fq.rs:849-902).  The reference runs a binary extended Euclid; the inverse is unique and the result is
+// canonical, so the algorithm is free: Bernstein-Yang division steps on signed 30-bit limbs (fp_inv_gcd.cuh), about a
+// tenth of the multiplier work of the Fermat power a^(q-2) that round 1 used (kept under -DBLS_FP_INV_FERMAT=1 for A/B
+// measurements).  Returns false (and zero) for a == 0, the reference's `None`.
+#ifndef BLS_FP_INV_FERMAT
+#define BLS_FP_INV_FERMAT 0
+#endif
+#if !BLS_FP_INV_FERMAT
+static __device__ __noinline__ bool fp_inv(Fp& out, const Fp& a) {
+  const Fp c = fp_canon(a);
+  gcd30::invert_words(out.v, c.v);
+  return !fp_is_zero_raw(c);
+}
+#else
+// a^(q-2) by a fixed 4-bit window over the (compile-time) exponent
 static __device__ __noinline__ bool fp_inv(Fp& out, const Fp& a) {
   if (fp_is_zero(a)) { out = fp_zero(); return false; }
   Fp tbl[16];
@@ -75,6 +88,7 @@ static __device__ __noinline__ bool fp_inv(Fp& out, const Fp& a) {
   out = r;
   return true;
 }
+#endif
 
 // fq2.rs:138-155
 __device__ __forceinline__ bool fp2_inv(Fp2& out, const Fp2& a) {

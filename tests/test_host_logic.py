@@ -254,3 +254,36 @@ def test_generated_squaring_schedule():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_fp_sqr.py"), "--check"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "222 wide MACs" in r.stdout
+
+
+def test_division_step_inversion_host_build_matches_pow():
+    """pairing_b200/csrc/fp_inv_gcd.cuh (the Fq inversion every CUDA kernel runs; fq.rs:849-902 is a binary extended
+    Euclid with the same unique result) is plain integer C: compiled for the host here and compared with pow(a, -1, q)
+    on edge operands, short operands of every bit length and random ones; the embedded 30-bit-limb constants are
+    recomputed."""
+    import random
+    import re
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "pairing_b200", "csrc", "fp_inv_gcd.cuh")).read()
+    def limbs(name):
+        body = re.search(r"#define %s\s*\\\n\s*\{(.*?)\}" % name, hdr, re.S).group(1).replace("\\", "")
+        return sum(int(t, 16) << (30 * i) for i, t in enumerate(body.replace(",", " ").split()))
+    R = 1 << 384
+    assert limbs("BLS_GCD_Q30") == m.Q and limbs("BLS_GCD_R2_30") == R * R % m.Q
+    assert int(re.search(r"QINV30 = (0x[0-9a-f]+)u", hdr).group(1), 16) == pow(m.Q, -1, 1 << 30)
+    rng = random.Random(0xDEC0DE)
+    vals = [0, 1, 2, 3, m.Q - 1, m.Q - 2, (m.Q + 1) // 2, R % m.Q, R * R % m.Q]
+    vals += [rng.randrange(1 << k) % m.Q for k in range(1, 382) for _ in range(2)]
+    vals += [rng.randrange(m.Q) for _ in range(3000)]
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "inv")
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(root, "tests", "cpp", "test_fp_inv_gcd.cpp")],
+                              stderr=subprocess.DEVNULL)
+        out = subprocess.run([exe], input="".join("%096x\n" % v for v in vals), capture_output=True, text=True, check=True).stdout.split("\n")
+    assert len(out) >= len(vals)
+    for v, line in zip(vals, out):
+        got, batches = line.split()
+        assert int(got, 16) == (pow(v, -1, m.Q) * R * R % m.Q if v else 0), hex(v)
+        assert int(batches) <= 38          # (49 * 381 + 57) / 17 = 1101 division steps bound the loop: 37 batches of 30
