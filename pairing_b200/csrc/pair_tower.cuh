@@ -481,6 +481,12 @@ __device__ __forceinline__ bool p12_is_zero(const P12& a) {
 }
 
 // mod.rs:104-160
+// BLS_Y0_CYCLOTOMIC_SQR = 1 squares r with the 6-product cyclotomic routine instead of the generic 12-product one (the same
+// value).  Off: under bench.py's conditions (L2 flushed between launches) the fused kernel measured 45.3 - 45.5 ms with it and
+// 43.1 - 44.6 ms without, three boxes; back to back without the flush the two builds are equal (43.2 ms).
+#ifndef BLS_Y0_CYCLOTOMIC_SQR
+#define BLS_Y0_CYCLOTOMIC_SQR 0
+#endif
 __device__ __forceinline__ bool p_final_exponentiation(P12& out, const P12& in) {
   P12 f1 = in, f2, r;
   p12_conjugate(f1);
@@ -491,7 +497,11 @@ __device__ __forceinline__ bool p_final_exponentiation(P12& out, const P12& in) 
   p12_mul(r, r, f2);
   const uint64_t x = BLS_X_ABS;
   P12 y0, y1, y2, y3;
+#if BLS_Y0_CYCLOTOMIC_SQR
   p12_cyclotomic_sqr(y0, r);          // r is in the cyclotomic subgroup after the easy part: the same value as `square`
+#else
+  p12_sqr(y0, r);
+#endif
   p12_exp_by_x_hard(y1, y0, x);
   p12_exp_by_x_hard(y2, y1, x >> 1);
   y3 = r; p12_conjugate(y3);

@@ -33,7 +33,7 @@ fn main() {
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
     println!("cargo:rustc-link-lib=dylib=pthread");
-    for f in &["kernels.cu", "kernels_pair.cu", "kernels_mm.cu", "kernels_wide.cu", "mgpu.cu", "abi_common.cuh", "pair_io.cuh", "fr.cuh", "fp.cuh", "fp_sqr_gen.cuh", "tower.cuh", "curve.cuh",
+    for f in &["kernels.cu", "kernels_pair.cu", "kernels_mm.cu", "kernels_wide.cu", "mgpu.cu", "abi_common.cuh", "pair_io.cuh", "fr.cuh", "fp.cuh", "fp_inv_gcd.cuh", "fp_sqr_gen.cuh", "tower.cuh", "curve.cuh",
                "pair_tower.cuh", "wide.cuh", "wide_prog_gen.cuh", "codec.cuh", "constants.cuh"] {
         println!("cargo:rerun-if-changed={}", root.join("pairing_b200/csrc").join(f).display());
     }

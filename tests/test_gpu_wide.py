@@ -61,7 +61,17 @@ def test_final_exponentiation_small_batches(path_ctx):
     f = dg.rand_field(70, 12, 303)
     f[4] = 0                       # None (mod.rs:107-108)
     f[5:40] = o.miller_loop(dg.g1_affine_points(35, 304), dg.g2_affine_points(35, 305), TH)
+    # operands whose easy part lands on one (or on another element with a zero c1.c0 coefficient): the compressed
+    # squarings of exp_by_x cannot be decompressed there and the lane-pair kernel has to take its uncompressed path --
+    # inside warps whose other lane pairs stay on the compressed one
+    one = np.zeros(72, dtype=np.uint64); one[:6] = np.array(m.limbs64(m.MONT_R), dtype=np.uint64)
+    f[41] = one
+    f[42, 36:] = 0                 # an element of Fq6
+    f[43, 12:] = 0                 # an element of Fq2
+    f[44] = 0; f[44, :6] = np.array(m.limbs64(m.Q - m.MONT_R), dtype=np.uint64)       # minus one
+    f[45, :36] = 0                 # c0 = 0: f = c1 w, f^(q^6 - 1) = -1
     want, wok = o.final_exponentiation(f, TH)
+    assert np.array_equal(want[41], one) and np.array_equal(want[42], one) and np.array_equal(want[45], one)
     got, gok = path_ctx.final_exponentiation(f)
     eq(got, want)
     assert np.array_equal(gok, wok) and gok[4] == 0
