@@ -188,8 +188,17 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_final_exp(
 // Field::pow on Fq12 with an FrRepr exponent (lib.rs:306-324; GT exponentiation, tests/engine.rs:121).  The reference
 // is MSB-first square-and-multiply; the value of a power does not depend on the addition chain, so this is a 4-bit
 // fixed window: 252 squarings + 64 table products, and -- the exponent differing per lane pair while every lane has to
-// reach every shuffle -- completely uniform control flow (a zero window multiplies by table[0] = one).  Generic
-// squaring: the input need not be in the cyclotomic subgroup.
+// reach every shuffle -- completely uniform control flow (a zero window multiplies by table[0] = one).
+// The operand of Field::pow may be any Fq12 element, but what callers raise to powers are GT elements (pairing values),
+// which lie in the cyclotomic subgroup a^(q^4 - q^2 + 1) = 1.  One Frobenius test per operand -- a^(q^4) a == a^(q^2),
+// about 1 % of the work -- tells: when it holds for every lane pair of the WARP, the 252 squarings are Granger-Scott
+// cyclotomic squarings (6 Fq2 products instead of 12, the same value there); otherwise the warp squares generically.
+__device__ __forceinline__ bool p12_eq(const P12& a, const P12& b) {
+  const bool e = fp_eq(a.c0.c0.v, b.c0.c0.v) && fp_eq(a.c0.c1.v, b.c0.c1.v) && fp_eq(a.c0.c2.v, b.c0.c2.v) &&
+                 fp_eq(a.c1.c0.v, b.c1.c0.v) && fp_eq(a.c1.c1.v, b.c1.c1.v) && fp_eq(a.c1.c2.v, b.c1.c2.v);
+  const int eo = __shfl_xor_sync(0xffffffffu, (int)e, 1);
+  return e && eo;
+}
 __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_fq12_pow(const uint64_t* in, const uint64_t* k, uint64_t* out, size_t n) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t i = t >> 1;
@@ -198,13 +207,22 @@ __global__ void __launch_bounds__(BLS_PAIR_TPB, BLS_PAIR_MINB) k_pair_fq12_pow(c
   P12 tbl[16];
   p12_one(tbl[0]);
   ld_p12(tbl[1], in + FQ12_W * i);
+  bool cyclotomic;
+  {
+    P12 f4, f2;
+    p12_frobenius(f4, tbl[1], 4);
+    p12_frobenius(f2, tbl[1], 2);
+    p12_mul(f4, f4, tbl[1]);
+    cyclotomic = __all_sync(0xffffffffu, p12_eq(f4, f2));
+  }
 #pragma unroll 1
   for (int e = 2; e < 16; e++) p12_mul(tbl[e], tbl[e - 1], tbl[1]);
   const Scalar s = ld_scalar(k + 4 * i);
   P12 res = tbl[(s.v[7] >> 28) & 0xf];
 #pragma unroll 1
   for (int w = 62; w >= 0; w--) {
-    p12_sqr(res, res); p12_sqr(res, res); p12_sqr(res, res); p12_sqr(res, res);
+    if (cyclotomic) { p12_cyclotomic_sqr(res, res); p12_cyclotomic_sqr(res, res); p12_cyclotomic_sqr(res, res); p12_cyclotomic_sqr(res, res); }
+    else { p12_sqr(res, res); p12_sqr(res, res); p12_sqr(res, res); p12_sqr(res, res); }
     const uint32_t nib = (s.v[w >> 3] >> ((w & 7) * 4)) & 0xf;
     p12_mul(res, res, tbl[nib]);
   }

@@ -285,6 +285,12 @@ def test_fq12_pow_and_bilinearity(ctx):
     assert not np.array_equal(lhs, one)
     r = np.repeat(np.array([m.limbs64(m.R_ORDER, 4)], dtype=np.uint64), n, 0)     # GT has order r
     eq(ctx.fq12_pow(lhs, r), one)
+    # the kernel squares with the cyclotomic routine when every operand of a warp passes its Frobenius test: GT operands
+    # alone (that path) and GT operands mixed with arbitrary field elements inside one warp (the generic path) vs the oracle
+    gt = ctx.pairing(pa, qa)
+    eq(ctx.fq12_pow(gt, k), _oracle_fq12_pow(gt, k))
+    mixed = gt.copy(); mixed[::5] = f[::5]
+    eq(ctx.fq12_pow(mixed, k), _oracle_fq12_pow(mixed, k))
 
 
 @pytest.mark.parametrize("op", ["add", "sub", "mul", "sqr", "neg", "dbl", "inv", "from_repr", "into_repr"])
