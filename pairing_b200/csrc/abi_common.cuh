@@ -61,6 +61,7 @@ struct bls_ctx {
   int device;
   int sm_count;
   cudaStream_t stream;
+  cudaStream_t stream2;                          // second kernel stream of run_pipelined (kernels of consecutive chunks overlap their tails)
   cudaStream_t copy_in, copy_out;                // the H2D / D2H legs of the chunked host-buffer entry points (run_pipelined)
   cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
   cudaMemPool_t pool;                            // staging buffers of the host-buffer entry points: cached across calls

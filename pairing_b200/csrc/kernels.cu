@@ -617,7 +617,7 @@ bls_ctx* bls_ctx_create(int device, int* err) {
   ctx->wide_final_exp_max = BLS_WIDE_FINAL_EXP_MAX;
   ctx->last_error[0] = 0;
   DevGuard guard;
-  ctx->stream = ctx->copy_in = ctx->copy_out = nullptr;
+  ctx->stream = ctx->stream2 = ctx->copy_in = ctx->copy_out = nullptr;
   ctx->pool = nullptr;
   for (int k = 0; k < 2; k++) ctx->ev_in[k] = ctx->ev_k[k] = ctx->ev_out[k] = nullptr;
   cudaMemPoolProps props = {};
@@ -629,6 +629,7 @@ bls_ctx* bls_ctx_create(int device, int* err) {
   bool ok = guard.enter(device) == cudaSuccess &&
             cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
             cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMemPoolCreate(&ctx->pool, &props) == cudaSuccess &&
@@ -650,7 +651,7 @@ void bls_ctx_destroy(bls_ctx* ctx) {
   if (!ctx) return;
   DevGuard guard;
   guard.enter(ctx->device);
-  for (cudaStream_t s : {ctx->stream, ctx->copy_in, ctx->copy_out})
+  for (cudaStream_t s : {ctx->stream, ctx->stream2, ctx->copy_in, ctx->copy_out})
     if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
   for (int k = 0; k < 2; k++)
     for (cudaEvent_t e : {ctx->ev_in[k], ctx->ev_k[k], ctx->ev_out[k]})
@@ -857,8 +858,12 @@ int bls_g2_batch_normalization_dev(bls_ctx* ctx, bls_g2* inout, size_t n, void* 
 namespace {
 struct PipeIn { const void* host; size_t stride; };
 template <class Launch>
-int run_pipelined(bls_ctx* ctx, size_t n, size_t chunk, const PipeIn* in, int n_in, void* host_out, size_t out_stride, Launch launch) {
+int run_pipelined(bls_ctx* ctx, size_t n, size_t chunk, const PipeIn* in, int n_in, void* host_out, size_t out_stride, Launch launch, bool two_kernel_streams = false) {
   const size_t nchunks = (n + chunk - 1) / chunk;
+  // two_kernel_streams: the kernels of consecutive chunks go to two streams, so that the blocks of chunk c + 1 fill the SMs as the
+  // last wave of chunk c drains (one launch over the whole batch would do the same) while the D2H of chunk c already runs.  Only
+  // for launches that share no scratch between chunks.
+  cudaStream_t ks[2] = {ctx->stream, two_kernel_streams ? ctx->stream2 : ctx->stream};
   DevBuf din[2][3] = {{DevBuf(ctx), DevBuf(ctx), DevBuf(ctx)}, {DevBuf(ctx), DevBuf(ctx), DevBuf(ctx)}};
   DevBuf dout[2] = {DevBuf(ctx), DevBuf(ctx)};
   const size_t csz = n < chunk ? n : chunk;
@@ -869,6 +874,7 @@ int run_pipelined(bls_ctx* ctx, size_t n, size_t chunk, const PipeIn* in, int n_
   CK(cudaEventRecord(ctx->ev_k[0], ctx->stream));      // the allocations are ordered on ctx->stream: the copy streams wait for them
   CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_k[0], 0));
   CK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[0], 0));
+  if (two_kernel_streams) CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_k[0], 0));
   for (size_t c = 0; c < nchunks; c++) {
     const int b = (int)(c & 1);
     const size_t lo = c * chunk, cn = (n - lo) < chunk ? (n - lo) : chunk;
@@ -876,20 +882,28 @@ int run_pipelined(bls_ctx* ctx, size_t n, size_t chunk, const PipeIn* in, int n_
     for (int k = 0; k < n_in; k++)
       CK(cudaMemcpyAsync(din[b][k].p, (const char*)in[k].host + lo * in[k].stride, cn * in[k].stride, cudaMemcpyHostToDevice, ctx->copy_in));
     CK(cudaEventRecord(ctx->ev_in[b], ctx->copy_in));
-    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[b], 0));
-    if (c >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[b], 0));         // the D2H of chunk c - 2 has drained this output set
+    CK(cudaStreamWaitEvent(ks[b], ctx->ev_in[b], 0));
+    if (c >= 2) CK(cudaStreamWaitEvent(ks[b], ctx->ev_out[b], 0));                // the D2H of chunk c - 2 has drained this output set
     const void* ptrs[3] = {din[b][0].p, din[b][1].p, din[b][2].p};
-    TRY(launch(ptrs, dout[b].p, cn));
-    CK(cudaEventRecord(ctx->ev_k[b], ctx->stream));
+    TRY(launch(ptrs, dout[b].p, cn, ks[b]));
+    CK(cudaEventRecord(ctx->ev_k[b], ks[b]));
     CK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_k[b], 0));
     CK(cudaMemcpyAsync((char*)host_out + lo * out_stride, dout[b].p, cn * out_stride, cudaMemcpyDeviceToHost, ctx->copy_out));
     CK(cudaEventRecord(ctx->ev_out[b], ctx->copy_out));
   }
   CK(cudaStreamSynchronize(ctx->copy_out));
+  if (two_kernel_streams) CK(cudaStreamSynchronize(ctx->stream2));
   CK(cudaStreamSynchronize(ctx->stream));              // the staging buffers are freed in ctx->stream order
   return BLS_OK;
 }
-const size_t PIPE_CHUNK_PAIRINGS = (size_t)1 << 16;     // one full launch of the pairing kernel per chunk (3.46 waves)
+// pairings per chunk of the host-buffer pairing / Miller-loop calls: ONE wave of the lane-pair kernels (2 blocks of 64 lane pairs
+// per SM, pair_io.cuh) -- 18 944 on a B200.  The chunk kernels alternate between two streams (run_pipelined), so a 2^16 batch still
+// runs as 3.46 back-to-back waves, but only the first chunk's H2D (5.8 MB) and the last chunk's D2H are exposed instead of the
+// whole 19.9 MB in and 37.7 MB out.
+#ifndef BLS_PIPE_TWO_STREAMS
+#define BLS_PIPE_TWO_STREAMS 1      /* 0: one kernel stream, one 2^16 launch per chunk (the first build of round 2; kept for A/B runs) */
+#endif
+static size_t pipe_chunk_pairings(const bls_ctx* ctx) { return BLS_PIPE_TWO_STREAMS ? (size_t)ctx->sm_count * 128 : (size_t)1 << 16; }
 const size_t PIPE_CHUNK_POINTS = (size_t)1 << 21;
 }  // namespace
 
@@ -912,18 +926,18 @@ static int miller_like(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine
   if (!n) return BLS_OK;
   USE_DEVICE(ctx);
   const PipeIn in[2] = {{p, sizeof(*p)}, {q, sizeof(*q)}};
-  return run_pipelined(ctx, n, PIPE_CHUNK_PAIRINGS, in, 2, out, sizeof(*out), [&](const void* const* d, void* o, size_t cn) -> int {
-    return final_exp ? bls_pairing_dev(ctx, (const bls_g1_affine*)d[0], (const bls_g2_affine*)d[1], (bls_fq12*)o, cn, nullptr)
-                     : bls_miller_loop_dev(ctx, (const bls_g1_affine*)d[0], (const bls_g2_affine*)d[1], (bls_fq12*)o, cn, nullptr);
-  });
+  return run_pipelined(ctx, n, pipe_chunk_pairings(ctx), in, 2, out, sizeof(*out), [&](const void* const* d, void* o, size_t cn, cudaStream_t s) -> int {
+    return final_exp ? bls_pairing_dev(ctx, (const bls_g1_affine*)d[0], (const bls_g2_affine*)d[1], (bls_fq12*)o, cn, s)
+                     : bls_miller_loop_dev(ctx, (const bls_g1_affine*)d[0], (const bls_g2_affine*)d[1], (bls_fq12*)o, cn, s);
+  }, BLS_PIPE_TWO_STREAMS != 0);
 }
 int bls_pairing_projective_batch(bls_ctx* ctx, const bls_g1* p, const bls_g2* q, bls_fq12* out, size_t n) {
   if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   USE_DEVICE(ctx);
   const PipeIn in[2] = {{p, sizeof(*p)}, {q, sizeof(*q)}};
-  return run_pipelined(ctx, n, PIPE_CHUNK_PAIRINGS, in, 2, out, sizeof(*out), [&](const void* const* d, void* o, size_t cn) -> int {
-    return bls_pairing_projective_dev(ctx, (const bls_g1*)d[0], (const bls_g2*)d[1], (bls_fq12*)o, cn, nullptr);
+  return run_pipelined(ctx, n, (size_t)1 << 16, in, 2, out, sizeof(*out), [&](const void* const* d, void* o, size_t cn, cudaStream_t s) -> int {
+    return bls_pairing_projective_dev(ctx, (const bls_g1*)d[0], (const bls_g2*)d[1], (bls_fq12*)o, cn, s);
   });
 }
 int bls_miller_loop_batch(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n) { return miller_like(ctx, p, q, out, n, false); }
@@ -1036,16 +1050,16 @@ static int wnaf_host(bls_ctx* ctx, int degree, const void* bases, const bls_fr_r
   USE_DEVICE(ctx);
   size_t pb = degree == 2 ? sizeof(bls_g2) : sizeof(bls_g1);
   const PipeIn in[2] = {{bases, pb}, {k, sizeof(*k)}};
-  return run_pipelined(ctx, n, PIPE_CHUNK_POINTS, in, 2, out, pb, [&](const void* const* d, void* o, size_t cn) -> int {
+  return run_pipelined(ctx, n, PIPE_CHUNK_POINTS, in, 2, out, pb, [&](const void* const* d, void* o, size_t cn, cudaStream_t ks) -> int {
     if (mode == 0) {
-      if (degree == 2) return bls_g2_wnaf_mul_dev(ctx, (const bls_g2*)d[0], (const bls_fr_repr*)d[1], (bls_g2*)o, cn, window, nullptr);
-      return bls_g1_wnaf_mul_dev(ctx, (const bls_g1*)d[0], (const bls_fr_repr*)d[1], (bls_g1*)o, cn, window, nullptr);
+      if (degree == 2) return bls_g2_wnaf_mul_dev(ctx, (const bls_g2*)d[0], (const bls_fr_repr*)d[1], (bls_g2*)o, cn, window, ks);
+      return bls_g1_wnaf_mul_dev(ctx, (const bls_g1*)d[0], (const bls_fr_repr*)d[1], (bls_g1*)o, cn, window, ks);
     }
-    if (degree == 2) k_pt_mul<Fp2><<<blocks_for(cn, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)d[0], (const uint64_t*)d[1], (uint64_t*)o, cn);
-    else k_pt_mul<Fp><<<blocks_for(cn, TPB), TPB, 0, ctx->stream>>>((const uint64_t*)d[0], (const uint64_t*)d[1], (uint64_t*)o, cn);
+    if (degree == 2) k_pt_mul<Fp2><<<blocks_for(cn, TPB), TPB, 0, ks>>>((const uint64_t*)d[0], (const uint64_t*)d[1], (uint64_t*)o, cn);
+    else k_pt_mul<Fp><<<blocks_for(cn, TPB), TPB, 0, ks>>>((const uint64_t*)d[0], (const uint64_t*)d[1], (uint64_t*)o, cn);
     LAUNCH_CHECK();
     return BLS_OK;
-  });
+  }, BLS_PIPE_TWO_STREAMS != 0);
 }
 int bls_g1_wnaf_mul_batch(bls_ctx* ctx, const bls_g1* b, const bls_fr_repr* k, bls_g1* out, size_t n) { return wnaf_host(ctx, 1, b, k, out, n, 0, 0); }
 int bls_g2_wnaf_mul_batch(bls_ctx* ctx, const bls_g2* b, const bls_fr_repr* k, bls_g2* out, size_t n) { return wnaf_host(ctx, 2, b, k, out, n, 0, 0); }
@@ -1187,10 +1201,10 @@ static int bn_host(bls_ctx* ctx, int degree, void* inout, size_t n) {
   const size_t csz = n < PIPE_CHUNK_POINTS ? n : PIPE_CHUNK_POINTS;
   DALLOC(dscr, bls_batch_normalization_scratch_bytes(ctx, degree, csz));
   const PipeIn in[1] = {{inout, pb}};
-  return run_pipelined(ctx, n, PIPE_CHUNK_POINTS, in, 1, inout, pb, [&](const void* const* d, void* o, size_t cn) -> int {
-    CK(cudaMemcpyAsync(o, d[0], cn * pb, cudaMemcpyDeviceToDevice, ctx->stream));
-    if (degree == 2) return bls_g2_batch_normalization_dev(ctx, (bls_g2*)o, cn, dscr.p, nullptr);
-    return bls_g1_batch_normalization_dev(ctx, (bls_g1*)o, cn, dscr.p, nullptr);
+  return run_pipelined(ctx, n, PIPE_CHUNK_POINTS, in, 1, inout, pb, [&](const void* const* d, void* o, size_t cn, cudaStream_t ks) -> int {
+    CK(cudaMemcpyAsync(o, d[0], cn * pb, cudaMemcpyDeviceToDevice, ks));
+    if (degree == 2) return bls_g2_batch_normalization_dev(ctx, (bls_g2*)o, cn, dscr.p, ks);
+    return bls_g1_batch_normalization_dev(ctx, (bls_g1*)o, cn, dscr.p, ks);
   });
 }
 int bls_g1_batch_normalization(bls_ctx* ctx, bls_g1* inout, size_t n) { return bn_host(ctx, 1, inout, n); }
