@@ -28,7 +28,7 @@ if what == "g2wnaf":
     q2[:, :24] = qa[:, :24]; q2[:, 24:30] = g1j[:1, 12:18]
 if what in ("pow", "finalexp"):
     eng.ctx.set_latency_path_limits(0, 0)
-    f = eng.miller_loop_batch(pa, qa)
+    f = eng.pairing(pa, qa) if what == "pow" else eng.miller_loop_batch(pa, qa)      # GT operands for the powers (cyclotomic path)
 for _ in range(2):
     if what in ("pairing", "pairing_wide"):
         eng.pairing(pa, qa, out)
