@@ -39,6 +39,29 @@ def test_fq_ops(ctx, op):
     assert np.array_equal(gok, wok)
 
 
+def test_fq_inverse_division_steps(ctx):
+    """The Fq inversion of every kernel (pairing_b200/csrc/fp_inv_gcd.cuh: division steps on 30-bit limbs; the reference:
+    fq.rs:849-902) against pow(a, -1, q) computed here: operands of every bit length (the batch loop ends at a different
+    step for each lane of a warp), +-small values, and 2^15 random ones -- on the thread-per-element path and on lane pairs."""
+    import random
+    rng = random.Random(0x1F)
+    vals = [0, 1, 2, 3, m.Q - 1, m.Q - 2, m.Q - 3, (m.Q + 1) // 2, m.MONT_R, m.MONT_RINV]
+    vals += [rng.randrange(1, 1 << k) % m.Q for k in range(1, 382) for _ in range(4)]
+    vals += [m.Q - rng.randrange(1, 1 << k) for k in range(1, 64)]
+    vals += [rng.randrange(m.Q) for _ in range(1 << 15)]
+    a = np.array([m.limbs64(m.to_mont(v)) for v in vals], dtype=np.uint64)
+    want = np.array([m.limbs64(m.to_mont(pow(v, -1, m.Q)) if v else 0) for v in vals], dtype=np.uint64)
+    got, ok = ctx.field_op(1, "inv", a)
+    eq(got, want)
+    assert np.array_equal(ok, np.array([1 if v else 0 for v in vals], dtype=ok.dtype))
+    # lane pairs: x + 0 u inverts to x^-1 + 0 u through p2_inv (both lanes of a pair run the inversion of the norm x^2)
+    a2 = np.zeros((len(vals), 12), dtype=np.uint64); a2[:, :6] = a
+    w2 = np.zeros_like(a2); w2[:, :6] = want
+    got2, ok2 = ctx.pair_field_op(2, "inv", a2)
+    eq(got2, w2)
+    assert np.array_equal(ok2, ok)
+
+
 def test_fq_add_sub_cross_edges(ctx):
     e = _edge_fq()
     a = np.repeat(e, len(e), 0); b = np.tile(e, (len(e), 1))
