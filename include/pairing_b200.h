@@ -15,7 +15,8 @@
  * Ownership: the caller owns every buffer; nothing is retained after a call returns.
  * Errors: every function returns 0 on success or a negative bls_status; nothing unwinds across
  * the ABI.  There is no CPU fallback: without a CUDA device bls_ctx_create fails.
- * Threading: calls on one bls_ctx must be serialised by the caller (one ordered stream per device).
+ * Threading: a bls_ctx may be shared by several host threads -- every entry point holds the context's lock while it runs on the
+ * host, so concurrent calls serialise (one ordered stream per device); use one context per thread for concurrency.
  */
 #ifndef PAIRING_B200_H
 #define PAIRING_B200_H
@@ -69,7 +70,7 @@ uint64_t bls_ctx_launch_count(const bls_ctx* ctx);
 int bls_ctx_trim(bls_ctx*, size_t keep_bytes);
 /* bls_pairing_* / bls_final_exponentiation_* pick between two kernels by batch size: up to these many elements one WARP
  * works on each element (latency path: ~2 ms for one pairing or for a thousand, the crate's bench_pairing_full shape),
- * above them one lane pair does (throughput path: 9.9 ms of latency, 1.37 M pairings/s).  Same bits either way.
+ * above them one lane pair does (throughput path: 8.8 ms of latency, 1.49 M pairings/s).  Same bits either way.
  * 0 disables the latency path.  Defaults: 2560 / 2560 (where the two curves cross on a B200). */
 int bls_ctx_set_latency_path_limits(bls_ctx*, size_t max_pairings, size_t max_final_exps);
 

@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/pairing_b200.h"
 #include "tower.cuh"
 
@@ -58,6 +60,7 @@ __device__ __forceinline__ Scalar ld_scalar(const uint64_t* p) {
 // Host side: context
 // ------------------------------------------------------------------------------------------------
 struct bls_ctx {
+  std::recursive_mutex mu;                       // every entry point holds it while it runs on the host (USE_DEVICE): calls from several threads serialise
   int device;
   int sm_count;
   cudaStream_t stream;
@@ -103,8 +106,9 @@ struct DevGuard {
   }
   ~DevGuard() { if (switched) cudaSetDevice(prev); }
 };
-#define USE_DEVICE(ctx) \
-  DevGuard dev_guard_;  \
+#define USE_DEVICE(ctx)                                          \
+  std::lock_guard<std::recursive_mutex> ctx_lock_((ctx)->mu);    \
+  DevGuard dev_guard_;                                           \
   CK(dev_guard_.enter((ctx)->device))
 
 static inline unsigned blocks_for(size_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }

@@ -685,6 +685,7 @@ int bls_ctx_sm_count(const bls_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 uint64_t bls_ctx_launch_count(const bls_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int bls_ctx_set_latency_path_limits(bls_ctx* ctx, size_t max_pairings, size_t max_final_exps) {
   if (!ctx) return BLS_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::recursive_mutex> lock(ctx->mu);
   ctx->wide_pairing_max = max_pairings;
   ctx->wide_final_exp_max = max_final_exps;
   return BLS_OK;

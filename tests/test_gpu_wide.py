@@ -236,3 +236,32 @@ def test_lane_pair_cyclotomic_square(ctx):
     want, _ = o.fq12_op("sqr", g)
     got, _ = ctx.pair_field_op(12, "cyclotomic_sqr", g)
     eq(got, want)
+
+
+def test_one_context_shared_by_several_host_threads(ctx):
+    """Every entry point holds the context's lock while it runs on the host (abi_common.cuh: USE_DEVICE), so calls from
+    several threads on ONE bls_ctx serialise instead of interleaving their staging buffers and streams: four threads issue
+    different calls at once (ctypes releases the GIL) and every result equals the one computed alone."""
+    import threading
+    p, q = dg.g1_affine_points(3000, 901), dg.g2_affine_points(3000, 902)        # above the latency-path limit: chunked pipeline + lane-pair kernel
+    f = o.miller_loop(p[:40], q[:40], TH)
+    jobs = {
+        "pairing": lambda: ctx.pairing(p, q),
+        "pairing_small": lambda: ctx.pairing(p[:33], q[:33]),
+        "final_exp": lambda: ctx.final_exponentiation(f)[0],
+        "product": lambda: ctx.pairing_product(p[:500], q[:500])[0],
+    }
+    want = {k: fn() for k, fn in jobs.items()}
+    got, errs = {}, []
+    def run(k, fn):
+        try:
+            for _ in range(3):
+                got[k] = fn()
+        except Exception as e:       # noqa: BLE001 -- reported below
+            errs.append((k, e))
+    threads = [threading.Thread(target=run, args=kv) for kv in jobs.items()]
+    for t in threads: t.start()
+    for t in threads: t.join()
+    assert not errs, errs
+    for k in jobs:
+        assert np.array_equal(np.asarray(got[k]), np.asarray(want[k])), k
