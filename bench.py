@@ -493,6 +493,25 @@ def run_ours(args):
         ms_pow, _ = timed(lambda: eng.fq12_pow(gt, g1_scalars[:npow].contiguous()))
         secondary["gt_pow"] = entry(npow, ms_pow, (254 * 36 + 127 * 54) * 300, unit="powers/s",
                                     config="SURVEY 8f-4: Fq12::pow(FrRepr) for 2^14 GT elements per GPU")
+        # G1Compressed::into_affine (checked: square root, lexicographic y, subgroup test) through the host-buffer
+        # call -- bytes in host memory, affine rows + status back; wall clock around the call, H2D and D2H included
+        ndec = 1 << 18
+        dec_aff = np.ascontiguousarray(tile(pa, ndec).cpu().numpy().view(np.uint64))
+        dec_bytes = eng.ctx.encode(False, dec_aff, True)
+        import pairing_b200._native as nat
+        dec_buf = np.frombuffer(dec_bytes, dtype=np.uint8).copy()
+        dec_back, dec_status = np.zeros((ndec, 13), dtype=np.uint64), np.zeros(ndec, dtype=np.uint8)
+        def decode_call(count):
+            eng.ctx._check(eng.ctx._lib.bls_g1_decode_batch(eng.ctx._ctx, nat._p(dec_buf), 1, 1, nat._p(dec_back), nat._p(dec_status), count))
+        decode_call(4096)
+        barrier()
+        t0 = time.perf_counter()
+        decode_call(ndec)
+        ms_dec = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        barrier()
+        secondary["g1_decode_compressed_checked"] = entry(ndec, ms_dec, 4514 * 300, unit="points/s", round_trip=bool(np.array_equal(dec_back, dec_aff)) and not dec_status.any(),
+                                                          config="SURVEY 8f-2: 2^18 compressed G1 points per GPU decoded with curve and subgroup validation (ec.rs:760-868), host buffers; 4514 M per point is the reference's count (sqrt + multiplication by r), the kernel decides the subgroup with the endomorphism test")
+        del dec_aff, dec_bytes, dec_back, dec_buf
 
     # host copies for the single-process multi-device measurement below (rank 0 only)
     mg_host = None

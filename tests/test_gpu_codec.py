@@ -170,3 +170,45 @@ def test_affine_mul(ctx, g2):
     ref = (o.g2_op if g2 else o.g1_op)("mul", proj, k=k, threads=TH)
     to_aff = o.g2_into_affine if g2 else o.g1_into_affine
     assert np.array_equal(to_aff(got), to_aff(ref))
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_subgroup_test_on_cofactor_points(ctx, g2):
+    """The kernels decide subgroup membership with an endomorphism (codec.cuh: (beta x, y) = [-u^2]P on G1, psi(Q) = [u]Q on
+    G2) where the reference multiplies by r (ec.rs:142-144).  Same answer required on the points built to tell the two apart:
+    points of small prime order in the cofactor group, the cofactor part [r]P of random curve points, random curve points,
+    and their cofactor-cleared images (in the subgroup) -- statuses against the big-integer model's multiplication by r."""
+    import random
+    rng = random.Random(77 + g2)
+    F = m._F2 if g2 else m._F1
+    u = -m.BLS_X
+    h = (u**8 - 4 * u**7 + 5 * u**6 - 4 * u**4 + 6 * u**3 - 4 * u**2 - 4 * u + 13) // 9 if g2 else (u - 1) ** 2 // 3
+    small = [13, 23, 2713, 11953, 262069] if g2 else [3, 11, 10177, 859267]
+    assert all(h % l == 0 for l in small)
+
+    def curve_point():
+        while True:
+            x = (rng.randrange(m.Q), rng.randrange(m.Q)) if g2 else rng.randrange(m.Q)
+            p = m.get_point_from_x(x, bool(rng.getrandbits(1)), g2)
+            if p is not None:
+                return p
+
+    def aff(j):
+        return m.pt_to_affine(F, j)
+
+    pts = []
+    for l in small:                                   # order-l points (when the l-part of the random point is non-trivial)
+        for _ in range(2):
+            j = m.pt_mul(F, m.pt_from_affine(F, curve_point()), h * m.R_ORDER // l)
+            if not m.pt_is_zero(F, j):
+                pts.append(aff(j))
+    for _ in range(3 if g2 else 6):
+        p = curve_point()
+        pts.append(p)                                                      # full order
+        pts.append(aff(m.pt_mul(F, m.pt_from_affine(F, p), m.R_ORDER)))    # its cofactor part
+        pts.append(aff(m.pt_mul(F, m.pt_from_affine(F, p), h)))            # its r-part: in the subgroup
+    enc = [m.encode_point(p, g2, False) for p in pts]
+    want = [m.decode_point(e, g2, False, True)[0] for e in enc]
+    assert want.count(0) >= (3 if g2 else 6) and want.count(m.DEC_NOT_IN_SUBGROUP) >= len(pts) // 2
+    _, status = ctx.decode(g2, b"".join(enc), False, True)
+    assert status.tolist() == want
