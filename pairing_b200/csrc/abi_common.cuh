@@ -1,5 +1,6 @@
-// abi_common.cuh -- shared by the two translation units of the library (kernels_pair.cu: the lane-pair pairing
-// engine; kernels.cu: curve, field-op, codec and measurement kernels + the host-buffer entry points).
+// abi_common.cuh -- shared by the translation units of the library (kernels_pair.cu: the lane-pair pairing engine; kernels_mm.cu: the
+// multi-pairing Miller loop; kernels_wide.cu: the warp-cooperative engine; kernels.cu: curve, field-op, codec and measurement kernels +
+// the host-buffer entry points; mgpu.cu: several devices behind one call).
 // The pairing engine is compiled on its own so that ptxas' register allocation of the routines it shares with
 // nothing else (fp_mul2, p6_mul, ...) cannot be perturbed by unrelated kernels: a two-line change in curve.cuh was
 // measured to slow the fused pairing kernel by 4 % when everything lived in one module.
@@ -74,7 +75,7 @@ struct bls_ctx {
   char last_error[256];
 };
 // Defaults of the two limits: below them one WARP per element (~2 ms for one pairing or for a thousand) beats the lane-pair
-// throughput kernels (9.9 ms of latency, 1.37 M pairings/s); bls_ctx_set_latency_path_limits overrides them per context.
+// throughput kernels (8.8 ms of latency, 1.49 M pairings/s); bls_ctx_set_latency_path_limits overrides them per context.
 #ifndef BLS_WIDE_PAIRING_MAX
 #define BLS_WIDE_PAIRING_MAX 2560
 #endif
