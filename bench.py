@@ -379,6 +379,19 @@ def run_ours(args):
         secondary["single_pairing"] = {"latency_ms": ms_one, "batch_1000_ms": ms_k, "projective_inputs_latency_ms": ms_one_proj, "projective_inputs_batch_1000_ms": ms_k_proj, "value": world * 1000 / (ms_k * 1e-3), "unit": "pairings/s",
                                        "units_per_gpu": 1000, "ms": ms_k, "roofline_frac": 1000 / (ms_k * 1e-3) * MAC32_PER_PAIRING / peak_macs,
                                        "config": "configs[0]: one pairing and the 1000 pairings of bench_pairing_full, on the warp-cooperative kernel (one WARP per pairing)"}
+        # the signature-verification shape: final_exponentiation(miller_loop(a FEW pairs)) in one call -- Miller loops one warp per
+        # pair, fold and final exponentiation in the tail kernel (latency path), against the lane-pair multi-Miller kernel
+        prod_ms = {}
+        for npairs in (2, 64):
+            pp, qq = pa[:npairs].contiguous(), qa[:npairs].contiguous()
+            eng.pairing_product(pp, qq)
+            prod_ms["n%d_ms" % npairs], _ = timed(lambda: eng.pairing_product(pp, qq))
+        ctx.set_latency_path_limits(0, 0)
+        eng.pairing_product(pa[:2].contiguous(), qa[:2].contiguous())
+        prod_ms["n2_lane_pair_kernels_ms"], _ = timed(lambda: eng.pairing_product(pa[:2].contiguous(), qa[:2].contiguous()))
+        ctx.set_latency_path_limits(2560, 2560)
+        secondary["pairing_product_small"] = dict(prod_ms, value=world * 2 / (prod_ms["n2_ms"] * 1e-3), unit="pairings/s", units_per_gpu=2, ms=prod_ms["n2_ms"],
+                                                  config="one bls_pairing_product_dev call over 2 / 64 pairs (batch-verification of a single signature: a product of two pairings)")
         from pairing_b200 import dist as pdist
         # configs[2] as stated: ONE multi_miller_loop product of 2^20 pairs IN TOTAL, sharded over the ranks (strong scaling),
         # with one shared final exponentiation.  Per rank: Miller kernel (one partial per block) + fold to one 576-byte

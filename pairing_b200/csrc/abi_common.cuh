@@ -160,6 +160,7 @@ BLS_INTERNAL int bls_internal_product_passes(bls_ctx* ctx, const uint64_t* in, s
 BLS_INTERNAL size_t bls_internal_mm_lane_pairs(const bls_ctx* ctx, size_t n);
 BLS_INTERNAL int bls_internal_wide_final_exp(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out, uint8_t* is_some, size_t n, cudaStream_t s);
 BLS_INTERNAL int bls_internal_wide_pairing(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, cudaStream_t s);
+BLS_INTERNAL int bls_internal_wide_miller(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, cudaStream_t s);
 BLS_INTERNAL int bls_internal_wide_pairing_projective(bls_ctx* ctx, const bls_g1* p, const bls_g2* q, bls_fq12* out, size_t n, cudaStream_t s);
 BLS_INTERNAL int bls_internal_product_tail(bls_ctx* ctx, const bls_fq12* in, size_t count, bls_fq12* out1, int final_exp, uint8_t* is_some, cudaStream_t s);
 BLS_INTERNAL int bls_internal_multi_miller_prepared(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_prepared* qp, size_t n, bls_fq12* partials, cudaStream_t s);

@@ -275,10 +275,18 @@ static size_t mm_threads(const bls_ctx* ctx, size_t n) {
   t = (t + per_block - 1) / per_block * per_block;
   return t ? t : per_block;
 }
+// Products of at most this many pairs run their Miller loops one WARP per pair (kernels_wide.cu: k_wide_miller, ~1 ms) instead of one
+// lane pair per pair (4.5 ms of latency): the signature-verification shape -- a product of two or a few pairings -- is latency-bound.
+// Follows the context's latency-path limit for pairings, capped here because the single-block tail folds the values serially
+// (47 us per 64 values).
+#define BLS_WIDE_PRODUCT_CAP 1024
+static size_t mm_wide_limit(const bls_ctx* ctx) { return ctx->wide_pairing_max < BLS_WIDE_PRODUCT_CAP ? ctx->wide_pairing_max : BLS_WIDE_PRODUCT_CAP; }
 size_t bls_multi_miller_scratch_bytes(const bls_ctx* ctx, size_t n) {
   if (!ctx) return 0;
   size_t T = mm_threads(ctx, n);
-  return mm_rstate_words(n) * sizeof(uint32_t) + (T / MM_LP) * sizeof(bls_fq12);
+  size_t bytes = mm_rstate_words(n) * sizeof(uint32_t) + (T / MM_LP) * sizeof(bls_fq12);
+  const size_t wide = (n <= BLS_WIDE_PRODUCT_CAP ? n : 0) * sizeof(bls_fq12);      // one Miller value per pair on the latency path
+  return bytes > wide ? bytes : wide;
 }
 
 // mod.rs:40-102 over ONE n-pair call: the Miller kernel leaves one partial product per block, the tail kernel folds them
@@ -288,6 +296,10 @@ static int multi_miller_impl(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_
   USE_DEVICE(ctx);
   cudaStream_t s = pick(ctx, stream);
   if (n == 0) return bls_internal_product_tail(ctx, nullptr, 0, out1, final_exp, is_some, s);   // the empty product: one
+  if (n <= mm_wide_limit(ctx)) {                                                                // latency path: one warp per pair, then the tail
+    TRY(bls_internal_wide_miller(ctx, p, q, (bls_fq12*)scratch, n, s));
+    return bls_internal_product_tail(ctx, (const bls_fq12*)scratch, n, out1, final_exp, is_some, s);
+  }
   size_t T = mm_threads(ctx, n);
   uint32_t* rstate = (uint32_t*)scratch;
   uint64_t* partials = (uint64_t*)((char*)scratch + mm_rstate_words(n) * sizeof(uint32_t));

@@ -322,6 +322,7 @@ int bls_miller_loop_dev(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affin
   if (!ctx || (n && (!p || !q || !out))) return BLS_ERR_INVALID_ARGUMENT;
   if (!n) return BLS_OK;
   USE_DEVICE(ctx);
+  if (n <= ctx->wide_pairing_max) return bls_internal_wide_miller(ctx, p, q, out, n, pick(ctx, stream));
   CK(pair_miller_smem_optin<false>());
   k_pair_miller<false><<<blocks_for(2 * n, BLS_PAIR_TPB), BLS_PAIR_TPB, pair_miller_smem_bytes(), pick(ctx, stream)>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();

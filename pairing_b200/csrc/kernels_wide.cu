@@ -1,6 +1,7 @@
 // kernels_wide.cu -- the latency path: ONE WARP per element (wide.cuh runs the micro-programs of wide_prog_gen.cuh).
 //   k_wide_pairing      Engine::pairing for small batches (BASELINE configs[0]: benches/bls12_381/mod.rs:91-107)
 //   k_wide_final_exp    Engine::final_exponentiation for small batches (mod.rs:104-160)
+//   k_wide_miller       Engine::miller_loop for small batches and for the Miller values of a small multi-pairing product
 //   k_pair_product_tail the tail of a multi-pairing product: the product of the per-block / per-device partial Miller
 //                       values on lane pairs, then -- optionally -- ONE final exponentiation by warp 0
 // Its own translation unit (see abi_common.cuh): nothing here can perturb ptxas' allocation of the throughput kernels.
@@ -50,6 +51,29 @@ __global__ void __launch_bounds__(32) k_wide_pairing(const uint64_t* p, const ui
   if (lp < 6) {
     Fp v = wide_ld(wide_slots, WIDE_PAIRING_OUT[lp], c);
     if (!live) v = (lp == 0 && c == 0) ? fp_one() : fp_zero();     // mod.rs:49-54: the pair is skipped, e = final_exponentiation(one) = one
+    st_fp(out + FQ12_W * i + 12 * lp + 6 * c, v);
+  }
+}
+
+// Engine::miller_loop for one pair per warp (mod.rs:40-102): the MILLER program, i.e. the PAIRING program without the final
+// exponentiation.  Small batches of bls_miller_loop_dev, and the Miller values of a SMALL multi-pairing product (the signature-
+// verification shape: a product of two or a few pairings), which k_pair_product_tail then folds and exponentiates.
+__global__ void __launch_bounds__(32) k_wide_miller(const uint64_t* p, const uint64_t* q, uint64_t* out, size_t n) {
+  extern __shared__ __align__(16) uint32_t wide_slots[];
+  const size_t i = blockIdx.x;
+  if (i >= n) return;
+  const int lane = threadIdx.x & 31, lp = lane >> 1, c = lane & 1;
+  const uint64_t* pi = p + G1A_W * i;
+  const uint64_t* qi = q + G2A_W * i;
+  const bool live = pi[12] == 0 && qi[24] == 0;
+  if (lp < 2) wide_st(wide_slots, lp, c, c ? fp_zero() : ld_fp(pi + 6 * lp));
+  else if (lp < 4) wide_st(wide_slots, lp, c, ld_fp(qi + 12 * (lp - 2) + 6 * c));
+  wide_load_consts(wide_slots, WIDE_MILLER_CONST, WIDE_MILLER_NCONST);
+  __syncwarp();
+  wide_run(WIDE_MILLER_CODE, WIDE_MILLER_NROUNDS, wide_slots, WIDE_MILLER_NSLOTS);
+  if (lp < 6) {
+    Fp v = wide_ld(wide_slots, WIDE_MILLER_OUT[lp], c);
+    if (!live) v = (lp == 0 && c == 0) ? fp_one() : fp_zero();     // mod.rs:49-54: the pair is skipped, f stays one
     st_fp(out + FQ12_W * i + 12 * lp + 6 * c, v);
   }
 }
@@ -179,6 +203,11 @@ int bls_internal_wide_final_exp(bls_ctx* ctx, const bls_fq12* in, bls_fq12* out,
 }
 int bls_internal_wide_pairing(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, cudaStream_t s) {
   k_wide_pairing<<<(unsigned)n, 32, (WIDE_PAIRING_NSLOTS + 1) * WIDE_SLOT_BYTES, s>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
+  LAUNCH_CHECK();
+  return BLS_OK;
+}
+int bls_internal_wide_miller(bls_ctx* ctx, const bls_g1_affine* p, const bls_g2_affine* q, bls_fq12* out, size_t n, cudaStream_t s) {
+  k_wide_miller<<<(unsigned)n, 32, (WIDE_MILLER_NSLOTS + 1) * WIDE_SLOT_BYTES, s>>>((const uint64_t*)p, (const uint64_t*)q, (uint64_t*)out, n);
   LAUNCH_CHECK();
   return BLS_OK;
 }

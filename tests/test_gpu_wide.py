@@ -80,7 +80,8 @@ def test_final_exponentiation_small_batches(path_ctx):
 
 
 @pytest.mark.parametrize("n", [0, 1, 2, 7, 129, 1000, 20000])
-def test_pairing_product(ctx, n):
+def test_pairing_product(path_ctx, n):
+    ctx = path_ctx          # up to 1024 pairs the Miller loops run one WARP per pair (k_wide_miller) when the latency path is on
     """final_exponentiation(miller_loop(n pairs)) in one call: block-level partial products, tail kernel, final
     exponentiation on the warp-cooperative engine (mod.rs:40-160)"""
     base = 512
@@ -94,6 +95,15 @@ def test_pairing_product(ctx, n):
     eq(got, want)
     assert ok == bool(wok[0])
     eq(ctx.multi_miller_loop(p, q), mm)
+
+
+@pytest.mark.parametrize("n", [1, 3, 200])
+def test_miller_loop_small_batches(path_ctx, n):
+    """Engine::miller_loop for n independent pairs (mod.rs:40-102) on both paths: one warp per pair (k_wide_miller) and one
+    lane pair per pair (k_pair_miller<false>); pairs with a point at infinity give one"""
+    p = dg.g1_affine_points(max(n, 8), 311, infinity_at=(1,))[:n]
+    q = dg.g2_affine_points(max(n, 8), 312, infinity_at=(2,))[:n]
+    eq(path_ctx.miller_loop(p, q), o.miller_loop(p, q, TH))
 
 
 @pytest.mark.parametrize("count", [1, 2, 31, 32, 33, 64, 65, 300, 1000])

@@ -644,7 +644,7 @@ def run_program(name, inputs):
 
 
 # ------------------------------------------------------------------------------------------------ header
-def render(names=("FINAL_EXP", "PAIRING", "TO_AFFINE")):
+def render(names=("FINAL_EXP", "PAIRING", "TO_AFFINE", "MILLER")):
     out = ["// wide_prog_gen.cuh -- GENERATED by tools/wide_gen.py (do not edit; `python tools/wide_gen.py` rewrites it).",
            "// Micro-programs of the warp-cooperative tower engine (wide.cuh): u16 words, per round",
            "//   [kind | nops << 8, max A-terms | max B-terms << 8] then per micro-op [dst, 4 A-terms, 4 B-terms];",
