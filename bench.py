@@ -525,6 +525,36 @@ def run_ours(args):
         secondary["g1_decode_compressed_checked"] = entry(ndec, ms_dec, 4514 * 300, unit="points/s", round_trip=bool(np.array_equal(dec_back, dec_aff)) and not dec_status.any(),
                                                           config="SURVEY 8f-2: 2^18 compressed G1 points per GPU decoded with curve and subgroup validation (ec.rs:760-868), host buffers; 4514 M per point is the reference's count (sqrt + multiplication by r), the kernel decides the subgroup with the endomorphism test")
         del dec_aff, dec_bytes, dec_back, dec_buf
+        # the same for 2^16 compressed G2 points (Fq2 square root by Algorithm 9 of eprint 2012/685, psi(Q) = [u]Q as the subgroup test)
+        ndec2 = 1 << 16
+        dec_aff2 = np.ascontiguousarray(tile(qa, ndec2).cpu().numpy().view(np.uint64))
+        dec_buf2 = np.frombuffer(eng.ctx.encode(True, dec_aff2, True), dtype=np.uint8).copy()
+        dec_back2, dec_status2 = np.zeros((ndec2, 25), dtype=np.uint64), np.zeros(ndec2, dtype=np.uint8)
+        def decode2_call(count):
+            eng.ctx._check(eng.ctx._lib.bls_g2_decode_batch(eng.ctx._ctx, nat._p(dec_buf2), 1, 1, nat._p(dec_back2), nat._p(dec_status2), count))
+        decode2_call(2048)
+        barrier()
+        t0 = time.perf_counter()
+        decode2_call(ndec2)
+        ms_dec2 = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        barrier()
+        secondary["g2_decode_compressed_checked"] = {"value": world * ndec2 / (ms_dec2 * 1e-3), "unit": "points/s", "units_per_gpu": ndec2, "ms": ms_dec2,
+                                                     "round_trip": bool(np.array_equal(dec_back2, dec_aff2)) and not dec_status2.any(),
+                                                     "config": "SURVEY 8f-2: 2^16 compressed G2 points per GPU decoded with curve and subgroup validation (ec.rs:1419-1540), host buffers"}
+        del dec_aff2, dec_buf2, dec_back2
+        # CurveProjective::mul_assign (double-and-add, ec.rs:534-553) for 2^18 G1 points through the host-buffer call
+        nmul = 1 << 18
+        mul_b = np.ascontiguousarray(tile(g1_jac, nmul).cpu().numpy().view(np.uint64))
+        mul_k = np.ascontiguousarray(tile(g1_scalars, nmul).cpu().numpy().view(np.uint64))
+        eng.ctx.g1_mul(mul_b[:4096], mul_k[:4096])
+        barrier()
+        t0 = time.perf_counter()
+        eng.ctx.g1_mul(mul_b, mul_k)
+        ms_mul = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        barrier()
+        secondary["g1_mul_assign"] = entry(nmul, ms_mul, (254 * 7 + 127 * 16) * 300, unit="scalar-muls/s",
+                                           config="SURVEY 8f-3: mul_assign (double-and-add over the 255-bit scalar) for 2^18 G1 points per GPU, host buffers (wall clock, copies and the Python wrapper's allocations included)")
+        del mul_b, mul_k
 
     # host copies for the single-process multi-device measurement below (rank 0 only)
     mg_host = None

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out; O=gpurun_out
+timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-mgpu --no-wnaf-e2e 2>$O/r3o_bench.err | python -c "
+import sys, json
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'])
+for k in ('g1_decode_compressed_checked', 'g2_decode_compressed_checked', 'g1_mul_assign', 'gt_pow'): print(k, {kk: vv for kk, vv in d['secondary'][k].items() if kk not in ('config', 'cpu_baseline')})
+"; tail -3 $O/r3o_bench.err
