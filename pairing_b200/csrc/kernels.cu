@@ -346,16 +346,47 @@ __global__ void __launch_bounds__(128, BLS_WNAF_MINB) k_wnaf_fixed_base(const ui
   }
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) k_pt_mul(const uint64_t* bases, const uint64_t* k, uint64_t* out, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// CurveProjective::mul_assign (ec.rs:534-553): MSB-first double-and-add.  Its operation sequence -- a doubling per bit once the
+// leading one has been seen, an addition of the base when the bit is set -- is wnaf_exp's (wnaf.rs:49-71) with digits in {0, 1} and a
+// one-entry table, so it runs on the decoupled-lane runner of the wNAF kernel (K points per lane; lock-step SIMT would execute an
+// addition for every bit position as long as ANY lane of the warp has that bit set).  Same Jacobian triple as the reference.
+template <class F, int K> struct BaseTable {
+  Jac<F> b[K];
+  __device__ __forceinline__ Jac<F> get(int j, int) const { return b[j]; }
+};
+template <class F, bool IS_G2, int K>
+__global__ void __launch_bounds__(128, IS_G2 ? BLS_WNAF_MINB : BLS_WNAF_MINB_G1) k_pt_mul(const uint64_t* bases, const uint64_t* k, uint64_t* out, size_t n) {
+  const size_t T = (size_t)gridDim.x * blockDim.x;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int PW = 3 * FW<F>::W;
-  Jac<F> base;
-  ld_jac(base, bases + (size_t)PW * i);
-  Scalar s = ld_scalar(k + 4 * i);
-  pt_mul(base, s);
-  st_jac(out + (size_t)PW * i, base);
+  Jac<F> res[K];
+  BaseTable<F, K> table;
+  int8_t digits[K][260];
+  WnafState<K> st;
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    size_t i = t + (size_t)j * T;
+    const bool active = i < n;
+    if (!active) i = n - 1;
+    ld_jac(table.b[j], bases + (size_t)PW * i);
+    Scalar s = ld_scalar(k + 4 * i);
+    if (!active) {
+#pragma unroll
+      for (int w = 0; w < 8; w++) s.v[w] = 0;
+    }
+    const int nb = scalar_num_bits(s);
+#pragma unroll 1
+    for (int b = 0; b < nb; b++) digits[j][b] = (int8_t)((s.v[b >> 5] >> (b & 31)) & 1u);
+    st.i[j] = nb - 1;
+    st.found[j] = false; st.doubled[j] = false;
+    pt_set_zero(res[j]);
+  }
+  pt_wnaf_run_lazy<F, K>(res, table, digits, st);
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    const size_t i = t + (size_t)j * T;
+    if (i < n) st_jac(out + (size_t)PW * i, res[j]);
+  }
 }
 
 template <class F>
@@ -1056,8 +1087,8 @@ static int wnaf_host(bls_ctx* ctx, int degree, const void* bases, const bls_fr_r
       if (degree == 2) return bls_g2_wnaf_mul_dev(ctx, (const bls_g2*)d[0], (const bls_fr_repr*)d[1], (bls_g2*)o, cn, window, ks);
       return bls_g1_wnaf_mul_dev(ctx, (const bls_g1*)d[0], (const bls_fr_repr*)d[1], (bls_g1*)o, cn, window, ks);
     }
-    if (degree == 2) k_pt_mul<Fp2><<<blocks_for(cn, TPB), TPB, 0, ks>>>((const uint64_t*)d[0], (const uint64_t*)d[1], (uint64_t*)o, cn);
-    else k_pt_mul<Fp><<<blocks_for(cn, TPB), TPB, 0, ks>>>((const uint64_t*)d[0], (const uint64_t*)d[1], (uint64_t*)o, cn);
+    if (degree == 2) k_pt_mul<Fp2, true, BLS_WNAF_K_G2><<<blocks_for((cn + BLS_WNAF_K_G2 - 1) / BLS_WNAF_K_G2, TPB), TPB, 0, ks>>>((const uint64_t*)d[0], (const uint64_t*)d[1], (uint64_t*)o, cn);
+    else k_pt_mul<Fp, false, BLS_WNAF_K><<<blocks_for((cn + BLS_WNAF_K - 1) / BLS_WNAF_K, TPB), TPB, 0, ks>>>((const uint64_t*)d[0], (const uint64_t*)d[1], (uint64_t*)o, cn);
     LAUNCH_CHECK();
     return BLS_OK;
   }, BLS_PIPE_TWO_STREAMS != 0);

@@ -287,3 +287,18 @@ def test_division_step_inversion_host_build_matches_pow():
         got, batches = line.split()
         assert int(got, 16) == (pow(v, -1, m.Q) * R * R % m.Q if v else 0), hex(v)
         assert int(batches) <= 38          # (49 * 381 + 57) / 17 = 1101 division steps bound the loop: 37 batches of 30
+
+
+def test_mul_assign_is_wnaf_exp_over_the_bits():
+    """k_pt_mul runs CurveProjective::mul_assign (ec.rs:534-553) on the wNAF kernel's decoupled-lane runner: the claim that its
+    operation sequence is wnaf_exp's (wnaf.rs:49-71) with the scalar's bits as digits and a one-entry table, on the model --
+    the same Jacobian TRIPLE, not just the same point."""
+    import random
+    rng = random.Random(41)
+    for F, gen in ((m._F1, m.G1_GEN_AFFINE), (m._F2, m.G2_GEN_AFFINE)):
+        base = m.pt_double(F, m.pt_from_affine(F, gen))               # Z != 1
+        for k in (0, 1, 2, 3, m.R_ORDER - 1, (1 << 255) - 1, rng.randrange(m.R_ORDER), rng.randrange(1 << 64)):
+            bits = [(k >> i) & 1 for i in range(k.bit_length())]
+            assert m.wnaf_exp(F, [base], bits) == m.pt_mul(F, base, k)
+        zero = m.pt_zero(F)
+        assert m.wnaf_exp(F, [zero], [1, 0, 1, 1]) == m.pt_mul(F, zero, 0b1101)
