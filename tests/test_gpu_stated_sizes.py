@@ -119,3 +119,37 @@ def test_g2_wnaf_prepare_2_20_points(eng, points):
     s = slice(n - 4096, n)
     p = _tile(pa, 4096)
     assert torch.equal(eng.miller_loop_prepared_batch(p, prep[s]), eng.miller_loop_batch(p, aff[s].contiguous()))
+
+
+def test_host_buffer_pairing_call_in_chunks_on_two_streams(eng, points):
+    """bls_pairing_batch cuts a batch into one-wave chunks (sm_count x 128 pairings) whose kernels alternate between two streams
+    while the copies of the neighbouring chunks run (kernels.cu: run_pipelined): 2.4 waves from host buffers -- full chunks, a
+    partial one, and a tail small enough for the latency path -- equal the one-launch device-resident result row for row."""
+    wave = eng.ctx.sm_count * 128
+    n = 2 * wave + wave // 3 + 1000
+    pa, qa = points[0][:n].clone(), points[1][:n].clone()
+    pa[wave - 1, 12] = 1; qa[wave, 24] = 1; pa[n - 1, 12] = 1          # infinity members on both sides of a chunk boundary and at the end
+    want = _np(eng.pairing(pa, qa))
+    got = eng.ctx.pairing(_np(pa), _np(qa))
+    assert np.array_equal(got, want)
+    m2 = 2 * wave + 700                                                # last chunk of 700 pairings: warp-cooperative kernel
+    assert np.array_equal(eng.ctx.pairing(_np(pa[:m2]), _np(qa[:m2])), want[:m2])
+    ml = eng.ctx.miller_loop(_np(pa[:m2]), _np(qa[:m2]))
+    assert np.array_equal(ml, _np(eng.miller_loop_batch(pa[:m2].contiguous(), qa[:m2].contiguous())))
+
+
+def test_host_buffer_wnaf_and_mul_calls_in_chunks(eng, points):
+    """bls_g1_wnaf_mul_batch / bls_g1_mul_batch from host buffers: 2^21-point chunks on two kernel streams (run_pipelined) --
+    two chunks and a ragged third equal the device-resident results; wNAF and mul_assign agree after normalisation."""
+    n = (1 << 22) + 4321
+    bases = _tile(points[2], n)
+    k = _scalars(n, 0xBEEF, eng.device)
+    want = _np(eng.g1_wnaf_mul(bases, k))
+    got = eng.ctx.g1_wnaf_mul(_np(bases), _np(k))
+    assert np.array_equal(got, want)
+    m2 = (1 << 21) + 99
+    mul = eng.ctx.g1_mul(_np(bases[:m2]), _np(k[:m2]))
+    idx = np.r_[np.arange(0, 40), np.arange(40, m2, 1 << 12), m2 - 1]
+    assert np.array_equal(mul[idx], o.g1_op("mul", _np(bases[idx]), k=_np(k[idx]), threads=TH))
+    a = eng.ctx.g1_batch_normalization(mul[idx]); b = eng.ctx.g1_batch_normalization(got[idx])
+    assert np.array_equal(a, b)
