@@ -165,7 +165,7 @@ def test_resource_usage_of_the_throughput_kernels():
         assert hits, part
         return hits[0]
     fused = of("k_pair_millerILb1")
-    assert fused["REG"] == 255 and fused["STACK"] <= 6320 and fused["SHARED"] == 0, fused     # 2 blocks x 128 threads per SM; the stack holds the six compressed powers of exp_by_x
+    assert fused["REG"] == 255 and fused["STACK"] <= 5904 and fused["SHARED"] == 0, fused     # 2 blocks x 128 threads per SM; the stack holds the six compressed powers of exp_by_x
     mm = of("k_pair_multi_millerPK")
     assert mm["REG"] == 255 and mm["STACK"] <= 1968 and mm["SHARED"] <= 19456 + 1024, mm
     g1 = of("k_wnaf_mul_lazykIN3bls2FpELb0ELi3ELi8")
